@@ -1,0 +1,143 @@
+/*
+ * sepfwi.h -- C ABI of libsepfwi.so: the B200-native (sm_100a) replacement for the
+ * data-parallel hot path of seisfwi/SEP-2023 (2-D isotropic elastic velocity-stress
+ * FD propagator with CPML, its adjoint, and the FWI gradient built on it).
+ *
+ * Reference interfaces replaced (paths under DAS_Waveform_Inversion/Ops/FWI/Src/):
+ *   sepfwi_cufd      <- extern "C" cufd(...)                    libCUFD.h:6-10, libCUFD.cu:32-820
+ *                       (same argument list; `const std::string para_fname` becomes `const char*`)
+ *   sepfwi_create    <- Parameter / Cpml / Bnd constructors     Parameter.cpp:17-178, Cpml.cu:7-118,
+ *                                                               Boundary.cu:5-43 (done once, not per call)
+ *   sepfwi_set_model <- Model constructor + host transposes     Model.cu:15-93, libCUFD.cu:67-77
+ *   sepfwi_forward   <- cufd(calc_id = 2) shot loop             libCUFD.cu:170-347
+ *   sepfwi_gradient  <- cufd(calc_id = 0 / 1) shot loop         libCUFD.cu:170-724, 775-780
+ *   sepfwi_ring_*    <- Bnd::field_from_bnd / field_to_bnd      Boundary.cu:55-101, utilities.cu:362-425
+ *
+ * Plain C: pointers, sizes and POD structs only -- no torch, no C++ types.  All
+ * functions return 0 on success or a negative SEPFWI_E* code; sepfwi_last_error()
+ * returns a message for the calling thread.  Nothing in this library calls exit().
+ * There is no CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Threading: a handle is bound to one device and must be used by one thread at a
+ * time; different handles (one per GPU) may be used concurrently, as the
+ * reference does from OpenMP threads (Torch_Fwi.cpp:71).
+ */
+#ifndef SEPFWI_H
+#define SEPFWI_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEPFWI_OK          0
+#define SEPFWI_EINVAL     -1   /* bad argument / inconsistent sizes            */
+#define SEPFWI_ECUDA      -2   /* CUDA runtime error (message has the detail)  */
+#define SEPFWI_ECOURANT   -3   /* CFL number > 1 (utilities.cu:225-241)        */
+#define SEPFWI_EIO        -4   /* para/survey/Shot_*.bin file problem          */
+#define SEPFWI_ENOMEM     -5   /* device allocation failed                     */
+
+/* DAS component recorded as `ett` and injected by the adjoint. */
+#define SEPFWI_FIBER_EXX   0   /* horizontal fiber: vx[z,x]-vx[z,x-1]   (recording_exx, utilities.cu:593-602) */
+#define SEPFWI_FIBER_EZZ   1   /* vertical fiber:   vz[z,x]-vz[z-1,x]   (recording_ezz, utilities.cu:620-628) */
+
+/* Scheme flavour. */
+#define SEPFWI_FLAVOUR_CPML   0 /* TorchFWI: fp32, CPML, stress->source->velocity->record(it+1)               */
+#define SEPFWI_FLAVOUR_SPONGE 1 /* DAS_Waveform_Modeling elasticSolver: sponge, velocity->stress->source->record(it) */
+
+/* Output components of sepfwi_forward (bit mask). */
+#define SEPFWI_OUT_PR   1
+#define SEPFWI_OUT_VX   2
+#define SEPFWI_OUT_VZ   4
+#define SEPFWI_OUT_ETT  8
+#define SEPFWI_OUT_EXX 16      /* sponge flavour only: exx, ezz, exz divided by dx/dz */
+#define SEPFWI_OUT_EZZ 32
+#define SEPFWI_OUT_EXZ 64
+
+/* Pointer spaces. */
+#define SEPFWI_MEM_HOST    0
+#define SEPFWI_MEM_DEVICE  1
+
+typedef struct sepfwi_params {
+    int   nz, nx;          /* padded grid exactly as para_file.json: nz = nz_orig + 2 nPml + nPad, nx = nx_orig + 2 nPml */
+    int   nPml, nPad;      /* nPoints_pml, nPad (sponge flavour: nPml = ndamp, nPad = 0)                                */
+    int   nSteps;
+    float dz, dx, dt, f0;
+    int   fiber;           /* SEPFWI_FIBER_*                                                                           */
+    int   flavour;         /* SEPFWI_FLAVOUR_*                                                                         */
+    int   max_batch;       /* shots propagated concurrently on the device (>= 1)                                       */
+    int   max_nrec;        /* upper bound of receivers per shot                                                        */
+    int   with_adjoint;    /* 1: allocate boundary store + adjoint state (needed by sepfwi_gradient with_adj)          */
+    int   kernels;         /* 0: default (fastest validated path), 1: force the unfused baseline kernels               */
+    int   reserved[6];
+} sepfwi_params;
+
+typedef struct sepfwi_shot {
+    int   zs, xs;          /* source position, padded-grid indices (survey index + nPml, Src_Rec.cu:87,92)             */
+    int   nrec;
+    const int   *zrec;     /* HOST pointers, padded-grid indices (Src_Rec.cu:108,115)                                  */
+    const int   *xrec;
+    const float *stf;      /* HOST pointer, nSteps raw samples; the 0.001 end taper of Src_Rec.cu:137 is applied inside
+                              (CPML flavour).  Sponge flavour: used as given, amplitude dt/2 (elasticSolver.py:259-260)  */
+    float src_rxz;         /* sxx/szz ratio used by the stf gradient only (utilities.cu:719-730); reference default 1   */
+    const float *obs_ett;  /* [nrec][nSteps] observed DAS data (gradient only); space given by `mem`                   */
+    float *out[7];         /* forward: pr, vx, vz, ett, exx, ezz, exz traces [nrec][nSteps] (NULL = skip); space `mem`  */
+    float *gstf;           /* gradient: HOST pointer, nSteps floats (NULL = skip)                                      */
+    const float *weights;  /* optional HOST [nrec][3]: ett = w0*exx + w1*ezz + w2*exz (NULL = pure fiber component)    */
+} sepfwi_shot;
+
+typedef struct sepfwi_handle sepfwi_handle;
+
+const char *sepfwi_last_error(void);
+int sepfwi_version(void);
+
+int sepfwi_create(const sepfwi_params *p, int device, sepfwi_handle **out);
+int sepfwi_destroy(sepfwi_handle *h);
+
+/* lambda, mu in MPa, rho in kg/m^3, row-major [nz][nx] (the tensors FWIFunction receives,
+ * FWI_ops.py:46-51).  Sponge flavour: lambda, mu in Pa.  Computes the averaged
+ * coefficients and the CFL number; returns SEPFWI_ECOURANT if it exceeds 1. */
+int sepfwi_set_model(sepfwi_handle *h, const float *lam, const float *mu, const float *rho, int mem, void *stream);
+int sepfwi_courant(sepfwi_handle *h, float *courant);
+
+/* Forward modelling of `nshots` shots (any number; processed max_batch at a time). */
+int sepfwi_forward(sepfwi_handle *h, int nshots, const sepfwi_shot *shots, int mem, void *stream);
+
+/* Misfit (+ gradient when with_adj) of `nshots` shots.
+ *   misfit : HOST float, 0.5 * sum over shots and samples of (obs-syn)^2      (libCUFD.cu:427,776)
+ *   glam, gmu, grho : [nz][nx] row-major in space `mem`, OVERWRITTEN with the sum over the given shots
+ *                     (gradients w.r.t. the MPa inputs for lambda, mu: el_stress.cu:108-115)
+ * `syn_ett`, when non-NULL in shots[i].out[3], receives the synthetic traces. */
+int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *shots, int with_adj,
+                    float *misfit, float *glam, float *gmu, float *grho, int mem, void *stream);
+
+/* Drop-in for the reference's `cufd`: host pointers, reads para_file.json /
+ * survey_file.json, reads/writes Shot_{pr,vx,vz,ett}{id}.bin exactly like
+ * libCUFD.cu:215-223,755-769.  calc_id 0 = misfit, 1 = misfit + gradient, 2 = observed data.
+ * grad_stf rows are written at the LOCAL shot index like libCUFD.cu:671-673. */
+int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, float *grad_Den, float *grad_stf,
+                const float *Lambda, const float *Mu, const float *Den, const float *stf,
+                int calc_id, int gpu_id, int group_size, const int *shot_ids, const char *para_fname);
+
+/* Frees the handles (device memory) sepfwi_cufd caches between calls. */
+int sepfwi_cufd_clear_cache(void);
+
+/* Boundary-ring geometry and save/restore of one [nz][nx] host field -- exposed so the index
+ * map of utilities.cu:362-425 can be checked bit-exactly.  `bnd` is a HOST buffer of
+ * sepfwi_ring_len() floats. */
+int sepfwi_ring_len(const sepfwi_params *p);
+int sepfwi_ring_save(sepfwi_handle *h, const float *field, float *bnd);
+int sepfwi_ring_restore(sepfwi_handle *h, float *field, const float *bnd);
+
+/* Introspection for tests and the bench: CPML profiles as built on the host
+ * (order K, a, b, K_half, a_half, b_half; z arrays have nz-nPad entries), kernel launch count
+ * since creation, and device time of the last forward / backward time loops in ms. */
+int sepfwi_get_cpml(sepfwi_handle *h, int axis /*0=z,1=x*/, float *out6xN);
+long long sepfwi_launch_count(sepfwi_handle *h);
+int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

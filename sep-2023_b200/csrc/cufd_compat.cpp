@@ -1,0 +1,255 @@
+// cufd_compat.cpp -- sepfwi_cufd: drop-in for the reference's `extern "C" cufd` shot driver
+// (DAS_Waveform_Inversion/Ops/FWI/Src/libCUFD.cu:32-820) on top of the handle API.
+//
+// Same side channels as the reference: para_file.json (Parameter.cpp:17-178),
+// survey_file.json (Src_Rec.cu:20-282), Shot_{pr,vx,vz,ett}{id}.bin raw float32
+// [nrec][nSteps] in data_dir_name (libCUFD.cu:215-223,755-769).  Handles are cached per
+// (device, parameter set) so an L-BFGS loop pays the allocations once, not per evaluation.
+#include <cuda_runtime.h>
+#include <ctype.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sepfwi.h"
+
+namespace {
+
+// ---- a very small JSON reader (objects, arrays, numbers, strings, true/false/null) ----
+struct JVal {
+    enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
+    double num = 0;
+    bool b = false;
+    std::string str;
+    std::vector<JVal> arr;
+    std::vector<std::pair<std::string, JVal>> obj;
+    const JVal *get(const char *k) const
+    {
+        for (auto &kv : obj) if (kv.first == k) return &kv.second;
+        return nullptr;
+    }
+};
+
+struct JParser {
+    const char *p, *end;
+    bool ok = true;
+    void ws() { while (p < end && isspace((unsigned char)*p)) p++; }
+    bool lit(const char *s) { size_t n = strlen(s); if ((size_t)(end - p) >= n && !strncmp(p, s, n)) { p += n; return true; } return false; }
+    JVal parse()
+    {
+        JVal v;
+        ws();
+        if (p >= end) { ok = false; return v; }
+        if (*p == '{') {
+            v.kind = JVal::Obj; p++; ws();
+            if (p < end && *p == '}') { p++; return v; }
+            while (ok) {
+                ws();
+                JVal k = parse();
+                if (k.kind != JVal::Str) { ok = false; break; }
+                ws();
+                if (p >= end || *p != ':') { ok = false; break; }
+                p++;
+                v.obj.emplace_back(k.str, parse());
+                ws();
+                if (p < end && *p == ',') { p++; continue; }
+                if (p < end && *p == '}') { p++; break; }
+                ok = false;
+            }
+        } else if (*p == '[') {
+            v.kind = JVal::Arr; p++; ws();
+            if (p < end && *p == ']') { p++; return v; }
+            while (ok) {
+                v.arr.push_back(parse());
+                ws();
+                if (p < end && *p == ',') { p++; continue; }
+                if (p < end && *p == ']') { p++; break; }
+                ok = false;
+            }
+        } else if (*p == '"') {
+            v.kind = JVal::Str; p++;
+            while (p < end && *p != '"') {
+                if (*p == '\\' && p + 1 < end) { p++; v.str.push_back(*p == 'n' ? '\n' : *p == 't' ? '\t' : *p); }
+                else v.str.push_back(*p);
+                p++;
+            }
+            if (p >= end) ok = false; else p++;
+        } else if (lit("true")) { v.kind = JVal::Bool; v.b = true; }
+        else if (lit("false")) { v.kind = JVal::Bool; v.b = false; }
+        else if (lit("null")) { v.kind = JVal::Null; }
+        else {
+            char *q = nullptr;
+            v.kind = JVal::Num; v.num = strtod(p, &q);
+            if (q == p) ok = false; else p = q;
+        }
+        return v;
+    }
+};
+
+// Both reference parsers read only the first line of the file (getline, Parameter.cpp:29, Src_Rec.cu:32).
+bool read_first_line(const std::string &fname, std::string &line)
+{
+    FILE *fp = fopen(fname.c_str(), "rb");
+    if (!fp) return false;
+    line.clear();
+    int c;
+    while ((c = fgetc(fp)) != EOF && c != '\n') line.push_back((char)c);
+    fclose(fp);
+    return true;
+}
+
+struct Cached {
+    sepfwi_handle *h = nullptr;
+    ~Cached() { if (h) sepfwi_destroy(h); }
+};
+std::mutex g_mu;
+std::map<std::string, std::unique_ptr<Cached>> g_cache;
+
+int efail(int code, const std::string &msg);
+
+}  // namespace
+
+extern "C" int sepfwi_set_error_(int code, const char *msg);   // defined in sepfwi.cu
+
+namespace { int efail(int code, const std::string &msg) { return sepfwi_set_error_(code, msg.c_str()); } }
+
+extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, float *grad_Den, float *grad_stf,
+                           const float *Lambda, const float *Mu, const float *Den, const float *stf,
+                           int calc_id, int gpu_id, int group_size, const int *shot_ids, const char *para_fname)
+{
+    if (calc_id < 0 || calc_id > 2) return efail(SEPFWI_EINVAL, "Invalid calc_id");
+    if (!Lambda || !Mu || !Den || !stf || !shot_ids || !para_fname || group_size < 0) return efail(SEPFWI_EINVAL, "null argument");
+    std::string line;
+    if (!read_first_line(para_fname, line)) return efail(SEPFWI_EIO, std::string("Error opening parameter file ") + para_fname);
+    JParser jp{line.data(), line.data() + line.size()};
+    JVal para = jp.parse();
+    if (!jp.ok || para.kind != JVal::Obj) return efail(SEPFWI_EIO, "parameter file is not a JSON object");
+    auto num = [&](const char *k, double &out) { const JVal *v = para.get(k); if (!v || v->kind != JVal::Num) return false; out = v->num; return true; };
+    double nz, nx, dz, dx, nSteps, dt, f0, nPml, nPad;
+    if (!num("nz", nz) || !num("nx", nx) || !num("dz", dz) || !num("dx", dx) || !num("nSteps", nSteps) || !num("dt", dt) ||
+        !num("f0", f0) || !num("nPoints_pml", nPml) || !num("nPad", nPad))
+        return efail(SEPFWI_EIO, "parameter file lacks one of nz nx dz dx nSteps dt f0 nPoints_pml nPad");
+    const JVal *sv = para.get("survey_fname"), *dd = para.get("data_dir_name");
+    if (!sv || sv->kind != JVal::Str || !dd || dd->kind != JVal::Str) return efail(SEPFWI_EIO, "parameter file lacks survey_fname / data_dir_name");
+    int fiber = SEPFWI_FIBER_EXX;
+    if (const JVal *dc = para.get("das_component")) if (dc->kind == JVal::Str && dc->str == "ezz") fiber = SEPFWI_FIBER_EZZ;
+    double max_batch = 0;
+    num("max_batch", max_batch);
+
+    if (!read_first_line(sv->str, line)) return efail(SEPFWI_EIO, "Error opening survey file " + sv->str);
+    JParser js{line.data(), line.data() + line.size()};
+    JVal survey = js.parse();
+    if (!js.ok || survey.kind != JVal::Obj) return efail(SEPFWI_EIO, "survey file is not a JSON object");
+
+    const int nS = (int)nSteps, npml = (int)nPml;
+    struct ShotData { std::vector<int> zr, xr; std::vector<float> obs, out[4], gstf; };
+    std::vector<ShotData> sd(group_size);
+    std::vector<sepfwi_shot> shots(group_size);
+    int maxrec = 1;
+    for (int i = 0; i < group_size; i++) {
+        const std::string key = "shot" + std::to_string(shot_ids[i]);
+        const JVal *s = survey.get(key.c_str());
+        if (!s || s->kind != JVal::Obj) return efail(SEPFWI_EIO, "survey file lacks " + key);
+        const JVal *zs = s->get("z_src"), *xs = s->get("x_src"), *nr = s->get("nrec"), *zr = s->get("z_rec"), *xr = s->get("x_rec");
+        if (!zs || !xs || !nr || !zr || !xr || zr->kind != JVal::Arr || xr->kind != JVal::Arr) return efail(SEPFWI_EIO, key + " is incomplete");
+        const int nrec = (int)nr->num;
+        if ((int)zr->arr.size() < nrec || (int)xr->arr.size() < nrec) return efail(SEPFWI_EIO, key + ": fewer receiver coordinates than nrec");
+        sd[i].zr.resize(nrec); sd[i].xr.resize(nrec);
+        for (int r = 0; r < nrec; r++) { sd[i].zr[r] = (int)zr->arr[r].num + npml; sd[i].xr[r] = (int)xr->arr[r].num + npml; }   // Src_Rec.cu:108,115
+        sepfwi_shot &sh = shots[i];
+        memset(&sh, 0, sizeof(sh));
+        sh.zs = (int)zs->num + npml; sh.xs = (int)xs->num + npml;                                                               // Src_Rec.cu:87,92
+        sh.nrec = nrec; sh.zrec = sd[i].zr.data(); sh.xrec = sd[i].xr.data();
+        sh.stf = stf + (size_t)shot_ids[i] * nS;                                                                                // Src_Rec.cu:132
+        const JVal *rxz = s->get("src_rxz");
+        sh.src_rxz = rxz && rxz->kind == JVal::Num ? (float)rxz->num : 1.0f;                                                     // RSXXZZ, utilities.h:21
+        maxrec = nrec > maxrec ? nrec : maxrec;
+    }
+
+    // handle cache
+    char keybuf[512];
+    snprintf(keybuf, sizeof(keybuf), "%d|%d|%d|%d|%d|%d|%.9g|%.9g|%.9g|%.9g|%d|%d|%d", gpu_id, (int)nz, (int)nx, npml, (int)nPad, nS,
+             dz, dx, dt, f0, fiber, calc_id == 1, (int)max_batch);
+    std::unique_lock<std::mutex> lk(g_mu);
+    std::unique_ptr<Cached> &slot = g_cache[keybuf];
+    sepfwi_handle *h = slot ? slot->h : nullptr;
+    // a cached handle must be able to hold this call's receiver count
+    static std::map<std::string, int> cap;
+    if (h && cap[keybuf] < maxrec) { slot.reset(); h = nullptr; }
+    if (!h) {
+        sepfwi_params p;
+        memset(&p, 0, sizeof(p));
+        p.nz = (int)nz; p.nx = (int)nx; p.nPml = npml; p.nPad = (int)nPad; p.nSteps = nS;
+        p.dz = (float)dz; p.dx = (float)dx; p.dt = (float)dt; p.f0 = (float)f0;
+        p.fiber = fiber; p.flavour = SEPFWI_FLAVOUR_CPML; p.max_nrec = maxrec; p.with_adjoint = calc_id == 1;
+        int B = (int)max_batch;
+        if (B <= 0) {   // enough concurrent shots to give every launch a few million cells, within memory
+            const double cells = (double)(p.nz - p.nPad) * p.nx;
+            B = (int)(4.0e6 / cells) + 1;
+            if (B > 16) B = 16;
+            size_t fr = 0, tot = 0;
+            if (cudaSetDevice(gpu_id) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
+                const double per = (calc_id == 1 ? 5.0 * sepfwi_ring_len(&p) * nS * 4.0 + 29.0 * cells * 4.0 : 13.0 * cells * 4.0) +
+                                   4.0 * maxrec * nS * 4.0;
+                while (B > 1 && per * B > 0.6 * (double)fr) B--;
+            }
+        }
+        if (B > group_size && group_size > 0) B = group_size;
+        p.max_batch = B;
+        int rc = sepfwi_create(&p, gpu_id, &h);
+        if (rc) { g_cache.erase(keybuf); return rc; }
+        slot.reset(new Cached());
+        slot->h = h;
+        cap[keybuf] = maxrec;
+    }
+    lk.unlock();
+
+    int rc = sepfwi_set_model(h, Lambda, Mu, Den, SEPFWI_MEM_HOST, nullptr);
+    if (rc) return rc;
+
+    auto fname = [&](const char *comp, int id) { return dd->str + "/Shot_" + comp + std::to_string(id) + ".bin"; };
+    static const char *comps[4] = {"pr", "vx", "vz", "ett"};
+    if (calc_id == 2) {
+        for (int i = 0; i < group_size; i++)
+            for (int c = 0; c < 4; c++) { sd[i].out[c].assign((size_t)shots[i].nrec * nS, 0.f); shots[i].out[c] = sd[i].out[c].data(); }
+        rc = sepfwi_forward(h, group_size, shots.data(), SEPFWI_MEM_HOST, nullptr);
+        if (rc) return rc;
+        for (int i = 0; i < group_size; i++)
+            for (int c = 0; c < 4; c++) {
+                FILE *fp = fopen(fname(comps[c], shot_ids[i]).c_str(), "wb");
+                if (!fp) return efail(SEPFWI_EIO, "File writing error! " + fname(comps[c], shot_ids[i]));
+                fwrite(sd[i].out[c].data(), sizeof(float), sd[i].out[c].size(), fp);
+                fclose(fp);
+            }
+        return 0;
+    }
+    for (int i = 0; i < group_size; i++) {
+        sd[i].obs.assign((size_t)shots[i].nrec * nS, 0.f);
+        const std::string fn = fname("ett", shot_ids[i]);
+        FILE *fp = fopen(fn.c_str(), "rb");
+        if (!fp) return efail(SEPFWI_EIO, "File reading error! Attempted to read " + fn);
+        size_t got = fread(sd[i].obs.data(), sizeof(float), sd[i].obs.size(), fp);
+        (void)got;
+        fclose(fp);
+        shots[i].obs_ett = sd[i].obs.data();
+        if (calc_id == 1 && grad_stf) shots[i].gstf = grad_stf + (size_t)i * nS;   // LOCAL shot index, libCUFD.cu:671-673
+    }
+    float J = 0.f;
+    rc = sepfwi_gradient(h, group_size, shots.data(), calc_id == 1, &J, grad_Lambda, grad_Mu, grad_Den, SEPFWI_MEM_HOST, nullptr);
+    if (rc) return rc;
+    if (misfit) *misfit = J;
+    return 0;
+}
+
+// Drop every cached handle (frees device memory); safe to call at any time.
+extern "C" int sepfwi_cufd_clear_cache(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_cache.clear();
+    return 0;
+}

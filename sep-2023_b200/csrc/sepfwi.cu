@@ -1,0 +1,649 @@
+// sepfwi.cu -- host engine and C ABI of libsepfwi.so (see include/sepfwi.h).
+//
+// One handle per GPU owns persistent device arenas (state, boundary ring store, traces,
+// gradients) sized at creation; nothing is allocated, parsed or read from disk inside the
+// time loops -- the reference re-does all of that on every call (libCUFD.cu:47-152,215-223).
+// Shots are propagated `max_batch` at a time: every kernel takes the slot index from
+// blockIdx.z / blockIdx.y, so small grids still fill the 148 SMs.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sepfwi.h"
+#include "common.cuh"
+#include "kernels_base.cuh"
+
+using namespace sepfwi;
+
+static thread_local char g_err[1024] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? SEPFWI_ENOMEM : SEPFWI_ECUDA,           \
+                        "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));       \
+    } while (0)
+
+struct sepfwi_handle {
+    sepfwi_params p;
+    int device;
+    Dims d;
+    int B;                 // slots
+    bool sponge;
+    // device arenas
+    float *state = nullptr, *model = nullptr, *cz = nullptr, *cx = nullptr, *damp = nullptr;
+    float *ring = nullptr, *trace = nullptr, *grad = nullptr, *gstf = nullptr;
+    float *dense[3] = {nullptr, nullptr, nullptr};   // [nz][nx] staging for model in / gradient out
+    int *maxcp = nullptr;
+    double *partial = nullptr, *misfit = nullptr;
+    // slot tables (device) + pinned host mirrors
+    int *t_int = nullptr, *h_int = nullptr;          // packed ints
+    float *t_flt = nullptr, *h_flt = nullptr;        // packed floats
+    size_t n_int = 0, n_flt = 0;
+    SlotTab tab;
+    // offsets (in elements) of the packed tables
+    size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec;
+    size_t o_amp, o_rxz, o_w, o_injCoef;
+    bool use_w = false;
+    // host copies
+    std::vector<float> hcz, hcx;
+    float courant = 0.f;
+    bool have_model = false;
+    long long launches = 0;
+    cudaEvent_t ev[4];
+    float fwd_ms = 0.f, bwd_ms = 0.f;
+    static const int NBLK_RES = 64;
+};
+
+extern "C" const char *sepfwi_last_error(void) { return g_err; }
+// used by the other translation units of the library to report through the same channel
+extern "C" int sepfwi_set_error_(int code, const char *msg) { return fail(code, "%s", msg); }
+extern "C" int sepfwi_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------
+// CPML profiles on the host, same arithmetic as cpmlInit (utilities.cu:243-359): Rcoef 8e-4,
+// NPOWER 8, K_MAX 2, alpha_max = pi f0, profile 0.25 d + 0.75 d^8, CpAve fixed to 3000.
+// Output rows: 1/K, a, b, 1/K_half, a_half, b_half (K itself kept for sepfwi_get_cpml).
+static void build_cpml(int N, int nPml, float dh, float f0, float dt, std::vector<float> &out, std::vector<float> &Kraw)
+{
+    out.assign((size_t)NCOEF * N, 0.f);
+    Kraw.assign((size_t)2 * N, 1.f);
+    const double PI = 3.141592653589793238462643383279502884197169;
+    const float alpha_max = (float)(2.0 * PI * (f0 / 2.0));
+    const float npower = 8.0f, kmax = 2.0f, w1 = 0.25f, w2 = 0.75f;
+    const float thick = nPml * dh;
+    const float d0 = (float)(-(npower + 1) * 3000.0f * log(0.0008f) / (2.0 * thick));
+    auto prof = [&](float depth, float &damp, float &K, float &alpha) {
+        if (depth >= 0.0f) {
+            const float dn = depth / thick;
+            damp = (float)(d0 * (w1 * dn + w2 * pow(dn, npower) + 0.0f * pow(dn, 2 * npower)));
+            K = (float)(1.0 + (kmax - 1.0) * pow(dn, npower));
+            alpha = (float)(alpha_max * (1.0 - dn));
+        }
+    };
+    for (int i = 0; i < N; i++) {
+        float damp = 0.f, K = 1.f, alpha = 0.f, damph = 0.f, Kh = 1.f, alphah = 0.f;
+        prof((nPml - i) * dh, damp, K, alpha);
+        prof((float)((nPml - i - 0.5) * dh), damph, Kh, alphah);
+        prof((nPml - N + i) * dh, damp, K, alpha);
+        {   // the reference evaluates K_half on the right edge with powf (utilities.cu:323)
+            float depth = (float)((nPml - N + i + 0.5) * dh);
+            if (depth >= 0.0f) {
+                const float dn = depth / thick;
+                damph = (float)(d0 * (w1 * dn + w2 * pow(dn, npower) + 0.0f * pow(dn, 2 * npower)));
+                Kh = (float)(1.0 + (kmax - 1.0) * powf(dn, npower));
+                alphah = (float)(alpha_max * (1.0 - dn));
+            }
+        }
+        if (alpha < 0.f) alpha = 0.f;
+        if (alphah < 0.f) alphah = 0.f;
+        const float b = expf(-(damp / K + alpha) * dt), bh = expf(-(damph / Kh + alphah) * dt);
+        float a = 0.f, ah = 0.f;
+        if (fabs(damp) > 1.0e-6) a = (float)(damp * (b - 1.0) / (K * (damp + K * alpha)));
+        if (fabs(damph) > 1.0e-6) ah = (float)(damph * (bh - 1.0) / (Kh * (damph + Kh * alphah)));
+        out[(size_t)C_RK * N + i] = 1.0f / K;   out[(size_t)C_A * N + i] = a;   out[(size_t)C_B * N + i] = b;
+        out[(size_t)C_RKH * N + i] = 1.0f / Kh; out[(size_t)C_AH * N + i] = ah; out[(size_t)C_BH * N + i] = bh;
+        Kraw[i] = K; Kraw[N + i] = Kh;
+    }
+}
+
+// Source-time-function end taper, cuda_window without weights (utilities.cu:844-884), ratio 0.001.
+static void taper_stf(int nt, float dt, float ratio, float *s)
+{
+    const double PI = 3.141592653589793238462643383279502884197169;
+    const float t0 = 0.f, t3 = nt * dt, off = nt * dt * ratio;
+    if (2.0 * off >= t3 - t0) return;
+    const float t1 = t0 + off, t2 = t3 - off;
+    for (int i = 0; i < nt; i++) {
+        const float t = i * dt;
+        float w;
+        if (t >= t0 && t < t1) w = (float)sin(PI / 2.0 * (t - t0) / (t1 - t0));
+        else if (t >= t1 && t < t2) w = 1.0f;
+        else if (t >= t2 && t < t3) w = (float)cos(PI / 2.0 * (t - t2) / (t3 - t2));
+        else w = 0.0f;
+        s[i] *= w * w;
+    }
+}
+
+static int fill_dims(const sepfwi_params &p, Dims &d)
+{
+    if (p.nz <= 0 || p.nx <= 0 || p.nSteps < 2 || p.nPml < 4 || p.nPad < 0) return fail(SEPFWI_EINVAL, "bad grid parameters (need nPml >= 4, nSteps >= 2)");
+    if (!(p.dz > 0.f && p.dx > 0.f && p.dt > 0.f)) return fail(SEPFWI_EINVAL, "dz, dx, dt must be positive");
+    memset(&d, 0, sizeof(d));
+    d.nz = p.nz; d.nx = p.nx; d.nPml = p.nPml; d.nPad = p.nPad; d.nSteps = p.nSteps;
+    d.nzA = p.nz - p.nPad;
+    if (d.nzA - 2 * p.nPml < 8 || d.nx - 2 * p.nPml < 8) return fail(SEPFWI_EINVAL, "interior smaller than 8 cells");
+    d.ldx = (p.nx + 31) / 32 * 32;
+    d.z1 = d.nzA - 1 - p.nPml; d.x1 = p.nx - 1 - p.nPml;
+    d.nzB = d.nzA - 2 * p.nPml + 4; d.nxB = p.nx - 2 * p.nPml + 4;
+    d.ringLen = 2 * 5 * (d.nzB + d.nxB);
+    d.maxRec = p.max_nrec > 0 ? p.max_nrec : 1;
+    d.dt = p.dt;
+    d.c1z = (float)(9.0 / 8.0) / p.dz; d.c2z = (float)(1.0 / 24.0) / p.dz;
+    d.c1x = (float)(9.0 / 8.0) / p.dx; d.c2x = (float)(1.0 / 24.0) / p.dx;
+    d.rdz = 1.0f / p.dz; d.rdx = 1.0f / p.dx;
+    d.fsz = (size_t)d.nzA * d.ldx;
+    return 0;
+}
+
+extern "C" int sepfwi_ring_len(const sepfwi_params *p)
+{
+    if (!p) return fail(SEPFWI_EINVAL, "null params");
+    return 2 * 5 * ((p->nz - 2 * p->nPml - p->nPad + 4) + (p->nx - 2 * p->nPml + 4));
+}
+
+static KArgs kargs(const sepfwi_handle *h)
+{
+    KArgs a;
+    a.d = h->d; a.state = h->state; a.model = h->model; a.cz = h->cz; a.cx = h->cx; a.damp = h->damp;
+    a.ring = h->ring; a.trace = h->trace; a.grad = h->grad; a.gstf = h->gstf; a.t = h->tab;
+    if (!h->use_w) a.t.w = nullptr;
+    return a;
+}
+
+extern "C" int sepfwi_destroy(sepfwi_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    float *fp[] = {h->state, h->model, h->cz, h->cx, h->damp, h->ring, h->trace, h->grad, h->gstf,
+                   h->dense[0], h->dense[1], h->dense[2], h->t_flt};
+    for (float *q : fp) if (q) cudaFree(q);
+    if (h->maxcp) cudaFree(h->maxcp);
+    if (h->partial) cudaFree(h->partial);
+    if (h->misfit) cudaFree(h->misfit);
+    if (h->t_int) cudaFree(h->t_int);
+    if (h->h_int) cudaFreeHost(h->h_int);
+    if (h->h_flt) cudaFreeHost(h->h_flt);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return 0;
+}
+
+extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle **out)
+{
+    if (!pp || !out) return fail(SEPFWI_EINVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SEPFWI_ECUDA, "no CUDA device available (%s); libsepfwi has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SEPFWI_EINVAL, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    sepfwi_handle *h = new sepfwi_handle();
+    for (int i = 0; i < 4; i++) h->ev[i] = nullptr;
+    h->p = *pp; h->device = device;
+    h->sponge = pp->flavour == SEPFWI_FLAVOUR_SPONGE;
+    int rc = fill_dims(*pp, h->d);
+    if (rc) { delete h; return rc; }
+    h->B = std::max(1, pp->max_batch);
+    h->d.nTrace = h->sponge ? NTRACE : 4;
+    if (h->sponge && pp->with_adjoint) { delete h; return fail(SEPFWI_EINVAL, "the sponge flavour is forward-only (the reference has no adjoint for it)"); }
+    const Dims &d = h->d;
+    const int B = h->B;
+#define ALLOC(ptr, n)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e2 = cudaMalloc((void **)&(ptr), (n));                                               \
+        if (e2 != cudaSuccess) {                                                                         \
+            int c = fail(SEPFWI_ENOMEM, "cudaMalloc of %zu bytes for %s failed: %s", (size_t)(n), #ptr,  \
+                         cudaGetErrorString(e2));                                                        \
+            sepfwi_destroy(h);                                                                           \
+            return c;                                                                                    \
+        }                                                                                                \
+    } while (0)
+    h->d.sstride = (size_t)(pp->with_adjoint ? NSTATE : (NFIELD + NPSI)) * d.fsz;
+    ALLOC(h->state, (size_t)B * d.sstride * sizeof(float));
+    ALLOC(h->model, (size_t)NMODEL * d.fsz * sizeof(float));
+    ALLOC(h->cz, (size_t)NCOEF * d.nzA * sizeof(float));
+    ALLOC(h->cx, (size_t)NCOEF * d.nx * sizeof(float));
+    ALLOC(h->trace, (size_t)B * d.nTrace * d.maxRec * d.nSteps * sizeof(float));
+    ALLOC(h->gstf, (size_t)B * d.nSteps * sizeof(float));
+    for (int k = 0; k < 3; k++) ALLOC(h->dense[k], (size_t)d.nz * d.nx * sizeof(float));
+    ALLOC(h->maxcp, sizeof(int));
+    ALLOC(h->partial, (size_t)B * sepfwi_handle::NBLK_RES * sizeof(double));
+    ALLOC(h->misfit, (size_t)B * sizeof(double));
+    if (pp->with_adjoint) {
+        ALLOC(h->ring, (size_t)B * NFIELD * d.nSteps * d.ringLen * sizeof(float));
+        ALLOC(h->grad, (size_t)B * 3 * d.fsz * sizeof(float));
+    }
+    if (h->sponge) ALLOC(h->damp, d.fsz * sizeof(float));
+    CU(cudaMemset(h->model, 0, (size_t)NMODEL * d.fsz * sizeof(float)));
+
+    // packed slot tables
+    const int maxCon = 8 * d.maxRec, maxInj = maxCon;
+    size_t oi = 0;
+    auto takei = [&](size_t n) { size_t o = oi; oi += n; return o; };
+    h->o_zs = takei(B); h->o_xs = takei(B); h->o_nrec = takei(B);
+    h->o_zrec = takei((size_t)B * d.maxRec); h->o_xrec = takei((size_t)B * d.maxRec);
+    h->o_injN = takei(B); h->o_injCell = takei((size_t)B * maxInj); h->o_injField = takei((size_t)B * maxInj);
+    h->o_injPtr = takei((size_t)B * (maxInj + 1)); h->o_injRec = takei((size_t)B * maxCon);
+    h->n_int = oi;
+    size_t of = 0;
+    auto takef = [&](size_t n) { size_t o = of; of += n; return o; };
+    h->o_amp = takef((size_t)B * d.nSteps); h->o_rxz = takef(B); h->o_w = takef((size_t)B * d.maxRec * 3);
+    h->o_injCoef = takef((size_t)B * maxCon);
+    h->n_flt = of;
+    ALLOC(h->t_int, h->n_int * sizeof(int));
+    ALLOC(h->t_flt, h->n_flt * sizeof(float));
+    CU(cudaMallocHost((void **)&h->h_int, h->n_int * sizeof(int)));
+    CU(cudaMallocHost((void **)&h->h_flt, h->n_flt * sizeof(float)));
+    memset(h->h_int, 0, h->n_int * sizeof(int));
+    memset(h->h_flt, 0, h->n_flt * sizeof(float));
+    SlotTab &t = h->tab;
+    t.zs = h->t_int + h->o_zs; t.xs = h->t_int + h->o_xs; t.nrec = h->t_int + h->o_nrec;
+    t.zrec = h->t_int + h->o_zrec; t.xrec = h->t_int + h->o_xrec;
+    t.injN = h->t_int + h->o_injN; t.injCell = h->t_int + h->o_injCell; t.injField = h->t_int + h->o_injField;
+    t.injPtr = h->t_int + h->o_injPtr; t.injRec = h->t_int + h->o_injRec;
+    t.amp = h->t_flt + h->o_amp; t.rxz = h->t_flt + h->o_rxz; t.w = h->t_flt + h->o_w; t.injCoef = h->t_flt + h->o_injCoef;
+    t.maxInj = maxInj; t.maxCon = maxCon;
+
+    // CPML profiles / sponge
+    if (!h->sponge) {
+        std::vector<float> kz, kx;
+        build_cpml(d.nzA, d.nPml, pp->dz, pp->f0, pp->dt, h->hcz, kz);
+        build_cpml(d.nx, d.nPml, pp->dx, pp->f0, pp->dt, h->hcx, kx);
+        // keep raw K for introspection: store behind the six rows
+        h->hcz.insert(h->hcz.end(), kz.begin(), kz.end());
+        h->hcx.insert(h->hcx.end(), kx.begin(), kx.end());
+        CU(cudaMemcpy(h->cz, h->hcz.data(), (size_t)NCOEF * d.nzA * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->cx, h->hcx.data(), (size_t)NCOEF * d.nx * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        // multiplicative sponge sin^2(pi/2 i/ndamp) from all four sides, elasticSolver.py:74-79
+        std::vector<float> dm(d.fsz, 1.0f);
+        const int nd = d.nPml;
+        for (int z = 0; z < d.nzA; z++)
+            for (int x = 0; x < d.nx; x++) {
+                double v = 1.0;
+                auto w = [&](int i) { double s_ = sin(M_PI / 2 * i / nd); return s_ * s_; };
+                if (x < nd) v *= w(x);
+                if (x >= d.nx - nd) v *= w(d.nx - 1 - x);
+                if (z < nd) v *= w(z);
+                if (z >= d.nzA - nd) v *= w(d.nzA - 1 - z);
+                dm[(size_t)z * d.ldx + x] = (float)v;
+            }
+        CU(cudaMemcpy(h->damp, dm.data(), d.fsz * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < 4; i++) CU(cudaEventCreate(&h->ev[i]));
+    *out = h;
+    return 0;
+}
+
+extern "C" int sepfwi_get_cpml(sepfwi_handle *h, int axis, float *out)
+{
+    if (!h || !out || h->sponge) return fail(SEPFWI_EINVAL, "bad argument");
+    const int N = axis == 0 ? h->d.nzA : h->d.nx;
+    const std::vector<float> &c = axis == 0 ? h->hcz : h->hcx;
+    const float *K = c.data() + (size_t)NCOEF * N;
+    for (int i = 0; i < N; i++) {
+        out[0 * N + i] = K[i];           out[1 * N + i] = c[(size_t)C_A * N + i];  out[2 * N + i] = c[(size_t)C_B * N + i];
+        out[3 * N + i] = K[N + i];       out[4 * N + i] = c[(size_t)C_AH * N + i]; out[5 * N + i] = c[(size_t)C_BH * N + i];
+    }
+    return 0;
+}
+
+extern "C" long long sepfwi_launch_count(sepfwi_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms)
+{
+    if (!h) return fail(SEPFWI_EINVAL, "null handle");
+    if (fwd_ms) *fwd_ms = h->fwd_ms;
+    if (bwd_ms) *bwd_ms = h->bwd_ms;
+    return 0;
+}
+
+extern "C" int sepfwi_set_model(sepfwi_handle *h, const float *lam, const float *mu, const float *rho, int mem, void *stream)
+{
+    if (!h || !lam || !mu || !rho) return fail(SEPFWI_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims &d = h->d;
+    const size_t nb = (size_t)d.nz * d.nx * sizeof(float);
+    const float *src[3] = {lam, mu, rho};
+    const float *dev[3];
+    for (int k = 0; k < 3; k++) {
+        if (mem == SEPFWI_MEM_HOST) {
+            CU(cudaMemcpyAsync(h->dense[k], src[k], nb, cudaMemcpyHostToDevice, st));
+            dev[k] = h->dense[k];
+        } else dev[k] = src[k];
+    }
+    CU(cudaMemsetAsync(h->maxcp, 0, sizeof(int), st));
+    dim3 blk(32, 8), grd((d.nx + 31) / 32, (d.nz + 7) / 8);
+    if (h->sponge) k_model_prep<true><<<grd, blk, 0, st>>>(d, dev[0], dev[1], dev[2], h->model, h->maxcp);
+    else k_model_prep<false><<<grd, blk, 0, st>>>(d, dev[0], dev[1], dev[2], h->model, h->maxcp);
+    h->launches++;
+    CU(cudaGetLastError());
+    int bits = 0;
+    CU(cudaMemcpyAsync(&bits, h->maxcp, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    float cpmax;
+    memcpy(&cpmax, &bits, 4);
+    const float dh = h->p.dz < h->p.dx ? h->p.dz : h->p.dx;
+    h->courant = (float)(cpmax * h->p.dt * sqrtf(2.0f) * (1.0 / 24.0 + 9.0 / 8.0) / dh);   // utilities.cu:235
+    h->have_model = true;
+    if (h->courant > 1.0f) {
+        h->have_model = false;
+        return fail(SEPFWI_ECOURANT, "Courant_number = %g > 1 (max Cp %g, dt %g, dh %g)", h->courant, cpmax, h->p.dt, dh);
+    }
+    return 0;
+}
+
+extern "C" int sepfwi_courant(sepfwi_handle *h, float *c)
+{
+    if (!h || !c) return fail(SEPFWI_EINVAL, "null argument");
+    *c = h->courant;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-batch host staging of the slot tables.
+struct InjEntry { int field, cell, rec; float coef; };
+
+static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool need_inject, cudaStream_t st)
+{
+    const Dims &d = h->d;
+    const int maxCon = h->tab.maxCon, maxInj = h->tab.maxInj;
+    h->use_w = false;
+    for (int s = 0; s < nb; s++) if (shots[s].weights) h->use_w = true;
+    for (int s = 0; s < nb; s++) {
+        const sepfwi_shot &sh = shots[s];
+        if (sh.nrec < 0 || sh.nrec > d.maxRec) return fail(SEPFWI_EINVAL, "shot %d: nrec %d exceeds max_nrec %d", s, sh.nrec, d.maxRec);
+        if (sh.zs < 2 || sh.zs > d.nzA - 3 || sh.xs < 2 || sh.xs > d.nx - 3) return fail(SEPFWI_EINVAL, "shot %d: source (%d,%d) outside the active grid", s, sh.zs, sh.xs);
+        if (!sh.stf) return fail(SEPFWI_EINVAL, "shot %d: null stf", s);
+        if (sh.nrec > 0 && (!sh.zrec || !sh.xrec)) return fail(SEPFWI_EINVAL, "shot %d: null receiver arrays", s);
+        h->h_int[h->o_zs + s] = sh.zs; h->h_int[h->o_xs + s] = sh.xs; h->h_int[h->o_nrec + s] = sh.nrec;
+        for (int r = 0; r < sh.nrec; r++) {
+            const int z = sh.zrec[r], x = sh.xrec[r];
+            if (z < 1 || z > d.nzA - 2 || x < 1 || x > d.nx - 2) return fail(SEPFWI_EINVAL, "shot %d: receiver %d at (%d,%d) outside the grid", s, r, z, x);
+            h->h_int[h->o_zrec + (size_t)s * d.maxRec + r] = z;
+            h->h_int[h->o_xrec + (size_t)s * d.maxRec + r] = x;
+            float *w = h->h_flt + h->o_w + ((size_t)s * d.maxRec + r) * 3;
+            if (sh.weights) { w[0] = sh.weights[3 * r]; w[1] = sh.weights[3 * r + 1]; w[2] = sh.weights[3 * r + 2]; }
+            else { w[0] = h->p.fiber == SEPFWI_FIBER_EXX ? 1.f : 0.f; w[1] = h->p.fiber == SEPFWI_FIBER_EZZ ? 1.f : 0.f; w[2] = 0.f; }
+        }
+        // source amplitude per step
+        float *amp = h->h_flt + h->o_amp + (size_t)s * d.nSteps;
+        memcpy(amp, sh.stf, (size_t)d.nSteps * sizeof(float));
+        if (!h->sponge) {
+            taper_stf(d.nSteps, h->p.dt, 0.001f, amp);                       // Src_Rec.cu:137
+            const float scale = (float)pow(1500.0, 2);                       // utilities.cu:531
+            for (int it = 0; it < d.nSteps; it++) amp[it] = scale * amp[it] * h->p.dt;
+        } else {
+            for (int it = 0; it < d.nSteps; it++) amp[it] = (float)((double)amp[it] * (double)h->p.dt / 2.0);   // elasticSolver.py:259
+        }
+        h->h_flt[h->o_rxz + s] = sh.src_rxz;
+        if (need_inject) {
+            std::vector<InjEntry> v;
+            v.reserve((size_t)sh.nrec * 2);
+            for (int r = 0; r < sh.nrec; r++) {
+                const int z = sh.zrec[r], x = sh.xrec[r];
+                const float *w = h->h_flt + h->o_w + ((size_t)s * d.maxRec + r) * 3;
+                const int c = z * d.ldx + x;
+                if (w[0] != 0.f) { v.push_back({F_VX, c, r, w[0]}); v.push_back({F_VX, c - 1, r, -w[0]}); }
+                if (w[1] != 0.f) { v.push_back({F_VZ, c, r, w[1]}); v.push_back({F_VZ, c - d.ldx, r, -w[1]}); }
+                if (w[2] != 0.f) {
+                    v.push_back({F_VX, c + d.ldx, r, 0.5f * w[2]}); v.push_back({F_VX, c, r, -0.5f * w[2]});
+                    v.push_back({F_VZ, c + 1, r, 0.5f * w[2]});     v.push_back({F_VZ, c, r, -0.5f * w[2]});
+                }
+            }
+            std::stable_sort(v.begin(), v.end(), [](const InjEntry &a, const InjEntry &b) {
+                return a.field != b.field ? a.field < b.field : a.cell < b.cell; });
+            if ((int)v.size() > maxCon) return fail(SEPFWI_EINVAL, "too many injection terms");
+            int *cell = h->h_int + h->o_injCell + (size_t)s * maxInj, *fld = h->h_int + h->o_injField + (size_t)s * maxInj;
+            int *ptr = h->h_int + h->o_injPtr + (size_t)s * (maxInj + 1), *rec = h->h_int + h->o_injRec + (size_t)s * maxCon;
+            float *coef = h->h_flt + h->o_injCoef + (size_t)s * maxCon;
+            int nt = 0;
+            for (size_t k = 0; k < v.size(); k++) {
+                if (k == 0 || v[k].field != v[k - 1].field || v[k].cell != v[k - 1].cell) { cell[nt] = v[k].cell; fld[nt] = v[k].field; ptr[nt] = (int)k; nt++; }
+                rec[k] = v[k].rec; coef[k] = v[k].coef;
+            }
+            ptr[nt] = (int)v.size();
+            h->h_int[h->o_injN + s] = nt;
+        }
+    }
+    for (int s = nb; s < h->B; s++) { h->h_int[h->o_nrec + s] = 0; h->h_int[h->o_injN + s] = 0; }
+    CU(cudaMemcpyAsync(h->t_int, h->h_int, h->n_int * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->t_flt, h->h_flt, h->n_flt * sizeof(float), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+static int max_nrec(int nb, const sepfwi_shot *shots)
+{
+    int m = 0;
+    for (int s = 0; s < nb; s++) m = std::max(m, shots[s].nrec);
+    return m;
+}
+
+// Forward time loop of one batch.  CPML flavour: libCUFD.cu:268-332; sponge: elasticSolver.py:241-276.
+static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_ring, cudaStream_t st)
+{
+    const Dims &d = h->d;
+    KArgs a = kargs(h);
+    const size_t slot_stride = d.sstride * sizeof(float);
+    const size_t live = (size_t)(NFIELD + NPSI) * d.fsz * sizeof(float);
+    for (int s = 0; s < nb; s++)
+        CU(cudaMemsetAsync((char *)h->state + s * slot_stride, 0, live, st));
+    CU(cudaMemsetAsync(h->trace, 0, (size_t)nb * d.nTrace * d.maxRec * d.nSteps * sizeof(float), st));
+    dim3 blk(BX, BY), grd((d.nx + BX - 1) / BX, (d.nzA + BY - 1) / BY, nb);
+    dim3 rgrd((mrec + 127) / 128, nb), ringgrd((d.ringLen + 255) / 256, nb);
+    CU(cudaEventRecord(h->ev[0], st));
+    if (!h->sponge) {
+        for (int it = 0; it <= d.nSteps - 2; it++) {
+            if (save_ring) { k_ring_save<<<ringgrd, 256, 0, st>>>(a, it); h->launches++; }
+            k_stress_fwd<false><<<grd, blk, 0, st>>>(a, it);
+            k_velocity_fwd<false><<<grd, blk, 0, st>>>(a);
+            h->launches += 2;
+            if (mrec > 0) { k_record<false><<<rgrd, 128, 0, st>>>(a, it + 1, mask, h->p.fiber); h->launches++; }
+        }
+    } else {
+        for (int it = 0; it < d.nSteps; it++) {
+            k_velocity_fwd<true><<<grd, blk, 0, st>>>(a);
+            k_stress_fwd<true><<<grd, blk, 0, st>>>(a, it);
+            h->launches += 2;
+            if (mrec > 0) { k_record<true><<<rgrd, 128, 0, st>>>(a, it, mask, h->p.fiber); h->launches++; }
+        }
+    }
+    CU(cudaEventRecord(h->ev[1], st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sepfwi_forward(sepfwi_handle *h, int nshots, const sepfwi_shot *shots, int mem, void *stream)
+{
+    if (!h || !shots || nshots < 0) return fail(SEPFWI_EINVAL, "bad argument");
+    if (!h->have_model) return fail(SEPFWI_EINVAL, "sepfwi_set_model has not succeeded on this handle");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims &d = h->d;
+    const cudaMemcpyKind kind = mem == SEPFWI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    h->fwd_ms = 0.f; h->bwd_ms = 0.f;
+    for (int s0 = 0; s0 < nshots; s0 += h->B) {
+        const int nb = std::min(h->B, nshots - s0);
+        int mask = 0;
+        for (int s = 0; s < nb; s++)
+            for (int c = 0; c < NTRACE; c++)
+                if (shots[s0 + s].out[c]) {
+                    if (c >= d.nTrace) return fail(SEPFWI_EINVAL, "component %d is only available in the sponge flavour", c);
+                    mask |= 1 << c;
+                }
+        int rc = stage_batch(h, nb, shots + s0, false, st);
+        if (rc) return rc;
+        const int mrec = max_nrec(nb, shots + s0);
+        rc = run_forward(h, nb, mrec, mask, false, st);
+        if (rc) return rc;
+        for (int s = 0; s < nb; s++)
+            for (int c = 0; c < d.nTrace; c++)
+                if (shots[s0 + s].out[c] && shots[s0 + s].nrec > 0)
+                    CU(cudaMemcpyAsync(shots[s0 + s].out[c], h->trace + ((size_t)s * d.nTrace + c) * d.maxRec * d.nSteps,
+                                       (size_t)shots[s0 + s].nrec * d.nSteps * sizeof(float), kind, st));
+        CU(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        h->fwd_ms += ms;
+    }
+    return 0;
+}
+
+// Backward time loop of one batch, libCUFD.cu:500-653.
+static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
+{
+    const Dims &d = h->d;
+    KArgs a = kargs(h);
+    const size_t slot_stride = d.sstride * sizeof(float);
+    for (int s = 0; s < nb; s++)   // adjoint fields + adjoint memory variables restart from zero (libCUFD.cu:503-517)
+        CU(cudaMemsetAsync((char *)h->state + s * slot_stride + (size_t)S_ADJ * d.fsz * sizeof(float), 0,
+                           (size_t)(NFIELD + NPSI) * d.fsz * sizeof(float), st));
+    CU(cudaMemsetAsync(h->gstf, 0, (size_t)nb * d.nSteps * sizeof(float), st));
+    dim3 blk(BX, BY), grd((d.nx + BX - 1) / BX, (d.nzA + BY - 1) / BY, nb);
+    const int rx = d.x1 + 2 - (d.nPml - 2) + 1, rz = d.z1 + 2 - (d.nPml - 2) + 1;
+    dim3 rgrd((rx + BX - 1) / BX, (rz + BY - 1) / BY, nb);
+    dim3 igrd((minj + 127) / 128, nb);
+    CU(cudaEventRecord(h->ev[2], st));
+    for (int it = d.nSteps - 2; it >= 0; it--) {
+        k_velocity_bwd<<<rgrd, blk, 0, st>>>(a, it);
+        k_stress_bwd<<<rgrd, blk, 0, st>>>(a, it);
+        k_velocity_adj<<<grd, blk, 0, st>>>(a);
+        if (minj > 0) { k_inject<<<igrd, 128, 0, st>>>(a, it); h->launches++; }
+        k_stress_adj<<<grd, blk, 0, st>>>(a);
+        h->launches += 4;
+    }
+    CU(cudaEventRecord(h->ev[3], st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *shots, int with_adj,
+                               float *misfit, float *glam, float *gmu, float *grho, int mem, void *stream)
+{
+    if (!h || !shots || nshots < 0) return fail(SEPFWI_EINVAL, "bad argument");
+    if (!h->have_model) return fail(SEPFWI_EINVAL, "sepfwi_set_model has not succeeded on this handle");
+    if (h->sponge) return fail(SEPFWI_EINVAL, "the sponge flavour is forward-only");
+    if (with_adj && !h->p.with_adjoint) return fail(SEPFWI_EINVAL, "handle was created without with_adjoint");
+    if (with_adj && (!glam || !gmu || !grho)) return fail(SEPFWI_EINVAL, "null gradient output");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims &d = h->d;
+    const cudaMemcpyKind kin = mem == SEPFWI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind kout = mem == SEPFWI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (with_adj) CU(cudaMemsetAsync(h->grad, 0, (size_t)h->B * 3 * d.fsz * sizeof(float), st));
+    double J = 0.0;
+    h->fwd_ms = 0.f; h->bwd_ms = 0.f;
+    const size_t cs = (size_t)d.maxRec * d.nSteps;
+    for (int s0 = 0; s0 < nshots; s0 += h->B) {
+        const int nb = std::min(h->B, nshots - s0);
+        int rc = stage_batch(h, nb, shots + s0, with_adj != 0, st);
+        if (rc) return rc;
+        const int mrec = max_nrec(nb, shots + s0);
+        rc = run_forward(h, nb, mrec, 1 << T_ETT, with_adj != 0, st);
+        if (rc) return rc;
+        for (int s = 0; s < nb; s++) {
+            const sepfwi_shot &sh = shots[s0 + s];
+            if (sh.nrec > 0) {
+                if (!sh.obs_ett) return fail(SEPFWI_EINVAL, "shot %d: null obs_ett", s0 + s);
+                CU(cudaMemcpyAsync(h->trace + ((size_t)s * d.nTrace + T_OBS) * cs, sh.obs_ett,
+                                   (size_t)sh.nrec * d.nSteps * sizeof(float), kin, st));
+            }
+        }
+        KArgs a = kargs(h);
+        k_residual<<<dim3(sepfwi_handle::NBLK_RES, nb), 256, 0, st>>>(a, h->partial, sepfwi_handle::NBLK_RES);
+        k_sum_partials<<<1, 32 * ((nb + 31) / 32), 0, st>>>(h->partial, sepfwi_handle::NBLK_RES, h->misfit, nb);
+        h->launches += 2;
+        CU(cudaGetLastError());
+        std::vector<double> hj(nb);
+        CU(cudaMemcpyAsync(hj.data(), h->misfit, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        for (int s = 0; s < nb; s++)
+            if (shots[s0 + s].out[T_ETT] && shots[s0 + s].nrec > 0)
+                CU(cudaMemcpyAsync(shots[s0 + s].out[T_ETT], h->trace + ((size_t)s * d.nTrace + T_ETT) * cs,
+                                   (size_t)shots[s0 + s].nrec * d.nSteps * sizeof(float), kout, st));
+        if (with_adj) {
+            int minj = 0;
+            for (int s = 0; s < nb; s++) minj = std::max(minj, h->h_int[h->o_injN + s]);
+            rc = run_backward(h, nb, minj, st);
+            if (rc) return rc;
+        }
+        CU(cudaStreamSynchronize(st));
+        for (int s = 0; s < nb; s++) J += hj[s];
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        h->fwd_ms += ms;
+        if (with_adj) {
+            CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+            h->bwd_ms += ms;
+            for (int s = 0; s < nb; s++)
+                if (shots[s0 + s].gstf)
+                    CU(cudaMemcpy(shots[s0 + s].gstf, h->gstf + (size_t)s * d.nSteps, d.nSteps * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+    }
+    if (misfit) *misfit = (float)(0.5 * J);
+    if (with_adj) {
+        float *outs[3] = {glam, gmu, grho};
+        dim3 blk(32, 8), grd((d.nx + 31) / 32, (d.nz + 7) / 8);
+        for (int k = 0; k < 3; k++) {
+            float *dst = mem == SEPFWI_MEM_DEVICE ? outs[k] : h->dense[k];
+            k_grad_reduce<<<grd, blk, 0, st>>>(d, h->grad, h->B, k, dst);
+            h->launches++;
+            if (mem == SEPFWI_MEM_HOST)
+                CU(cudaMemcpyAsync(outs[k], dst, (size_t)d.nz * d.nx * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Ring save / restore of one host field (test entry points for the index map).
+static int ring_io(sepfwi_handle *h, float *field, float *bnd, int restore)
+{
+    if (!h || !field || !bnd) return fail(SEPFWI_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const Dims &d = h->d;
+    float *df = nullptr, *db = nullptr;
+    CU(cudaMalloc((void **)&df, d.fsz * sizeof(float)));
+    CU(cudaMalloc((void **)&db, (size_t)d.ringLen * sizeof(float)));
+    CU(cudaMemset(df, 0, d.fsz * sizeof(float)));
+    CU(cudaMemcpy2D(df, (size_t)d.ldx * sizeof(float), field, (size_t)d.nx * sizeof(float), (size_t)d.nx * sizeof(float), d.nzA, cudaMemcpyHostToDevice));
+    if (restore) CU(cudaMemcpy(db, bnd, (size_t)d.ringLen * sizeof(float), cudaMemcpyHostToDevice));
+    k_ring_copy_field<<<(d.ringLen + 255) / 256, 256>>>(d, df, db, restore);
+    h->launches++;
+    CU(cudaGetLastError());
+    if (restore) CU(cudaMemcpy2D(field, (size_t)d.nx * sizeof(float), df, (size_t)d.ldx * sizeof(float), (size_t)d.nx * sizeof(float), d.nzA, cudaMemcpyDeviceToHost));
+    else CU(cudaMemcpy(bnd, db, (size_t)d.ringLen * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(df); cudaFree(db);
+    return 0;
+}
+extern "C" int sepfwi_ring_save(sepfwi_handle *h, const float *field, float *bnd) { return ring_io(h, (float *)field, bnd, 0); }
+extern "C" int sepfwi_ring_restore(sepfwi_handle *h, float *field, const float *bnd) { return ring_io(h, field, (float *)bnd, 1); }

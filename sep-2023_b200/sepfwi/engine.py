@@ -1,0 +1,243 @@
+"""Propagator: thin Python owner of one libsepfwi handle (one GPU).
+
+Mirrors what the reference builds inside every `cufd` call -- Parameter, Model, Cpml,
+Bnd, Src_Rec (DAS_Waveform_Inversion/Ops/FWI/Src/libCUFD.cu:47-87) -- but as a persistent
+object, so an inversion pays for allocation and CPML set-up once.
+
+Arrays may be numpy arrays, CPU torch tensors (host path: the library copies) or CUDA
+torch tensors (zero-copy: the library reads / writes them in place on the current stream).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Params, Shot, check, lib
+
+_COMP = {"pr": _lib.T_PR, "vx": _lib.T_VX, "vz": _lib.T_VZ, "ett": _lib.T_ETT,
+         "exx": _lib.T_EXX, "ezz": _lib.T_EZZ, "exz": _lib.T_EXZ}
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _as_f32_host(a):
+    if _is_torch(a):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _as_i32(a):
+    if _is_torch(a):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class ShotSpec(object):
+    """One shot in padded-grid indices (survey index + nPml, Src_Rec.cu:87-115)."""
+
+    def __init__(self, zs, xs, zrec, xrec, stf, src_rxz=1.0, weights=None):
+        self.zs, self.xs = int(zs), int(xs)
+        self.zrec, self.xrec = _as_i32(zrec), _as_i32(xrec)
+        if self.zrec.shape != self.xrec.shape or self.zrec.ndim != 1:
+            raise ValueError("zrec and xrec must be 1-D arrays of equal length")
+        self.stf = _as_f32_host(stf)
+        self.src_rxz = float(src_rxz)
+        self.weights = None if weights is None else _as_f32_host(weights).reshape(-1, 3)
+        if self.weights is not None and self.weights.shape[0] != self.zrec.size:
+            raise ValueError("weights must be (nrec, 3)")
+
+    @property
+    def nrec(self):
+        return int(self.zrec.size)
+
+
+class Propagator(object):
+    def __init__(self, nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, fiber=_lib.FIBER_EXX,
+                 flavour=_lib.FLAVOUR_CPML, max_batch=1, max_nrec=1, with_adjoint=False, device=0, kernels=0):
+        self.params = Params(int(nz), int(nx), int(nPml), int(nPad), int(nSteps), float(dz), float(dx), float(dt),
+                             float(f0), int(fiber), int(flavour), int(max_batch), int(max_nrec),
+                             1 if with_adjoint else 0, int(kernels))
+        self.device = int(device)
+        self.nz, self.nx, self.nSteps = int(nz), int(nx), int(nSteps)
+        self._h = C.c_void_p()
+        check(lib().sepfwi_create(C.byref(self.params), self.device, C.byref(self._h)))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().sepfwi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _stream(self):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        except ImportError:
+            pass
+        return C.c_void_p(0)
+
+    def _ptr(self, a, keep):
+        """(pointer, is_device) of a float32 [..] array; host arrays are made contiguous and kept alive."""
+        if _is_torch(a) and a.is_cuda:
+            import torch
+            if a.dtype != torch.float32 or not a.is_contiguous():
+                a = a.detach().to(torch.float32).contiguous()
+            keep.append(a)
+            if a.device.index != self.device:
+                raise ValueError("tensor lives on cuda:%s, propagator on cuda:%d" % (a.device.index, self.device))
+            return a.data_ptr(), True
+        h = _as_f32_host(a)
+        keep.append(h)
+        return h.ctypes.data, False
+
+    # -- model --------------------------------------------------------------------------------
+    def set_model(self, lam, mu, rho):
+        """lam, mu [MPa] (sponge flavour: Pa), rho [kg/m^3]; (nz, nx) row-major float32."""
+        keep = []
+        ptrs = [self._ptr(a, keep) for a in (lam, mu, rho)]
+        for a in keep:
+            if tuple(a.shape) != (self.nz, self.nx):
+                raise ValueError("model arrays must have shape (%d, %d), got %s" % (self.nz, self.nx, tuple(a.shape)))
+        dev = [p[1] for p in ptrs]
+        if any(dev) and not all(dev):
+            raise ValueError("lam, mu, rho must all be on the host or all on the device")
+        check(lib().sepfwi_set_model(self._h, ptrs[0][0], ptrs[1][0], ptrs[2][0],
+                                     _lib.MEM_DEVICE if dev[0] else _lib.MEM_HOST, self._stream()))
+
+    @property
+    def courant(self):
+        c = C.c_float()
+        check(lib().sepfwi_courant(self._h, C.byref(c)))
+        return c.value
+
+    def cpml(self, axis):
+        n = (self.nz - self.params.nPad) if axis == 0 else self.nx
+        out = np.zeros((6, n), np.float32)
+        check(lib().sepfwi_get_cpml(self._h, axis, out.ctypes.data))
+        return dict(zip(["K", "a", "b", "K_half", "a_half", "b_half"], out))
+
+    @property
+    def launches(self):
+        return int(lib().sepfwi_launch_count(self._h))
+
+    def last_timing(self):
+        f, b = C.c_float(), C.c_float()
+        check(lib().sepfwi_last_timing(self._h, C.byref(f), C.byref(b)))
+        return f.value, b.value
+
+    def ring_len(self):
+        return int(lib().sepfwi_ring_len(C.byref(self.params)))
+
+    def ring_save(self, field):
+        f = _as_f32_host(field)
+        out = np.zeros(self.ring_len(), np.float32)
+        check(lib().sepfwi_ring_save(self._h, f.ctypes.data, out.ctypes.data))
+        return out
+
+    def ring_restore(self, field, bnd):
+        f = _as_f32_host(field).copy()
+        b = _as_f32_host(bnd)
+        check(lib().sepfwi_ring_restore(self._h, f.ctypes.data, b.ctypes.data))
+        return f
+
+    # -- shots ----------------------------------------------------------------------------------
+    def _shot_array(self, shots, keep):
+        arr = (Shot * len(shots))()
+        for k, s in enumerate(shots):
+            c = arr[k]
+            c.zs, c.xs, c.nrec = s.zs, s.xs, s.nrec
+            c.zrec, c.xrec, c.stf = s.zrec.ctypes.data, s.xrec.ctypes.data, s.stf.ctypes.data
+            if s.stf.size != self.nSteps:
+                raise ValueError("stf must have nSteps=%d samples, got %d" % (self.nSteps, s.stf.size))
+            c.src_rxz = s.src_rxz
+            if s.weights is not None:
+                c.weights = s.weights.ctypes.data
+            keep.append(s)
+        return arr
+
+    def forward(self, shots, comps=("pr", "vx", "vz", "ett"), device_out=False, out=None):
+        """Forward modelling.  Returns a list (one per shot) of {component: [nrec, nSteps] array}.
+        device_out=True returns CUDA torch tensors (no device->host copy).  `out` may supply
+        preallocated (e.g. pinned) host arrays: list of dicts like the return value."""
+        keep = []
+        arr = self._shot_array(shots, keep)
+        res = []
+        for k, s in enumerate(shots):
+            d = {}
+            for name in comps:
+                if out is not None:
+                    buf = out[k][name]
+                    ptr = buf.data_ptr() if _is_torch(buf) else buf.ctypes.data
+                elif device_out:
+                    import torch
+                    buf = torch.empty((s.nrec, self.nSteps), dtype=torch.float32, device="cuda:%d" % self.device)
+                    ptr = buf.data_ptr()
+                else:
+                    buf = np.empty((s.nrec, self.nSteps), np.float32)
+                    ptr = buf.ctypes.data
+                arr[k].out[_COMP[name]] = ptr
+                d[name] = buf
+            res.append(d)
+        check(lib().sepfwi_forward(self._h, len(shots), arr, _lib.MEM_DEVICE if device_out else _lib.MEM_HOST,
+                                   self._stream()))
+        return res
+
+    def gradient(self, shots, obs, with_adj=True, device=False, want_syn=False):
+        """Misfit and gradient of `shots` against observed DAS data `obs` (list of [nrec, nSteps]).
+        device=True: obs are CUDA tensors and the gradients are returned as CUDA tensors.
+        Returns dict(misfit, glam, gmu, grho, gstf[list], syn[list])."""
+        keep = []
+        arr = self._shot_array(shots, keep)
+        gstf, syn = [], []
+        for k, s in enumerate(shots):
+            p, is_dev = self._ptr(obs[k], keep)
+            if is_dev != bool(device):
+                raise ValueError("obs must live in the space selected by `device`")
+            if tuple(keep[-1].shape) != (s.nrec, self.nSteps):
+                raise ValueError("obs[%d] must have shape (%d, %d)" % (k, s.nrec, self.nSteps))
+            arr[k].obs_ett = p
+            if with_adj:
+                g = np.zeros(self.nSteps, np.float32)
+                arr[k].gstf = g.ctypes.data
+                gstf.append(g)
+            if want_syn:
+                if device:
+                    import torch
+                    b = torch.empty((s.nrec, self.nSteps), dtype=torch.float32, device="cuda:%d" % self.device)
+                    arr[k].out[_lib.T_ETT] = b.data_ptr()
+                else:
+                    b = np.empty((s.nrec, self.nSteps), np.float32)
+                    arr[k].out[_lib.T_ETT] = b.ctypes.data
+                syn.append(b)
+        misfit = C.c_float(0.0)
+        g3 = [None, None, None]
+        ptrs = [None, None, None]
+        if with_adj:
+            for k in range(3):
+                if device:
+                    import torch
+                    g3[k] = torch.empty((self.nz, self.nx), dtype=torch.float32, device="cuda:%d" % self.device)
+                    ptrs[k] = g3[k].data_ptr()
+                else:
+                    g3[k] = np.empty((self.nz, self.nx), np.float32)
+                    ptrs[k] = g3[k].ctypes.data
+        check(lib().sepfwi_gradient(self._h, len(shots), arr, 1 if with_adj else 0, C.byref(misfit),
+                                    ptrs[0], ptrs[1], ptrs[2], _lib.MEM_DEVICE if device else _lib.MEM_HOST,
+                                    self._stream()))
+        return dict(misfit=misfit.value, glam=g3[0], gmu=g3[1], grho=g3[2], gstf=gstf, syn=syn)

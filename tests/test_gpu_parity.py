@@ -1,0 +1,206 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI of
+libsepfwi.so; the checker is the CPU oracle, the committed golden vectors of the reference's
+CUDA path, and -- when oracle/_ref/libcufd_ref.so travelled with the snapshot -- the reference
+itself, run live on the same GPU.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import problems
+from util import cuda_shots, make_prop, oracle_observed, oracle_par, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances (relative L2).  fp32 on both sides; the CUDA path uses FMA contraction and
+# reciprocal multiplies where the oracle divides, so agreement is ~1e-6, not bit-exact.
+TOL_TRACE = 2e-5
+TOL_GRAD = 2e-4
+TOL_REF_TRACE = 1e-4      # north_star: seismograms within 1e-4
+TOL_REF_GRAD = 1e-3       # north_star: gradients within 1e-3 of the reference TorchFWI path
+
+
+def _mods():
+    from oracle import oracle as O
+    from sepfwi.engine import Propagator, ShotSpec
+    return O, Propagator, ShotSpec
+
+
+@pytest.mark.parametrize("mk,batch", [(problems.tiny, 1), (problems.tiny, 2), (problems.small, 3),
+                                      (lambda: problems.tiny(fiber=1), 2)])
+def test_forward_traces_match_oracle(mk, batch):
+    O, Propagator, ShotSpec = _mods()
+    prob = mk()
+    ref = oracle_observed(O, prob, comps=("pr", "vx", "vz", "ett"))
+    with make_prop(Propagator, prob, max_batch=batch) as P:
+        P.set_model(*prob.true)
+        assert abs(P.courant - O.courant(oracle_par(O, prob), *prob.true)) < 1e-6
+        out = P.forward(cuda_shots(prob, ShotSpec))
+        for sid in range(prob.nshots):
+            for c in ("pr", "vx", "vz", "ett"):
+                assert rel_l2(out[sid][c], ref[sid][c]) < TOL_TRACE, (prob.name, sid, c)
+                assert np.all(out[sid][c][:, 0] == 0.0)
+        assert P.launches > 0
+
+
+def test_cpml_profiles_match_oracle():
+    O, Propagator, _ = _mods()
+    prob = problems.small()
+    with make_prop(Propagator, prob) as P:
+        for axis, N, dh in ((0, prob.nz - prob.nPad, prob.dz), (1, prob.nx, prob.dx)):
+            mine, ref = P.cpml(axis), O.cpml(N, prob.nPml, dh, prob.f0, prob.dt)
+            for k in ref:
+                assert np.array_equal(mine[k], ref[k]), (axis, k)       # same host arithmetic: bit-exact
+
+
+def test_ring_layout_bit_exact():
+    """Boundary-save layout (utilities.cu:362-392) checked with an index-coded field: exact integers."""
+    O, Propagator, _ = _mods()
+    prob = problems.tiny()
+    par = oracle_par(O, prob)
+    cells = O.ring_cells(par)
+    field = (np.arange(prob.nz * prob.nx, dtype=np.float32)).reshape(prob.nz, prob.nx)   # exact in fp32
+    with make_prop(Propagator, prob) as P:
+        assert P.ring_len() == cells.shape[0]
+        bnd = P.ring_save(field)
+        assert np.array_equal(bnd, field[cells[:, 0], cells[:, 1]])
+        # restore: scatter a coded ring into a zero field, reference order (later entries win on corners)
+        code = np.arange(1, cells.shape[0] + 1, dtype=np.float32)
+        got = P.ring_restore(np.zeros_like(field), code)
+        want = np.zeros_like(field)
+        touched = np.zeros(field.shape, bool)
+        touched[cells[:, 0], cells[:, 1]] = True
+        assert np.array_equal(got != 0, touched)
+        # every restored value must be one of the codes that map to that cell
+        for idx in (0, 7, cells.shape[0] // 2, cells.shape[0] - 1):
+            z, x = cells[idx]
+            valid = code[(cells[:, 0] == z) & (cells[:, 1] == x)]
+            assert got[z, x] in valid
+
+
+@pytest.mark.parametrize("mk,batch", [(problems.tiny, 1), (problems.tiny, 2), (problems.small, 2),
+                                      (lambda: problems.tiny(fiber=1), 1)])
+def test_gradient_matches_oracle(mk, batch):
+    O, Propagator, ShotSpec = _mods()
+    prob = mk()
+    par = oracle_par(O, prob)
+    obs = {sid: v["ett"] for sid, v in oracle_observed(O, prob).items()}
+    J, gl, gm, gd, gs = O.fwi_backward(par, *prob.start, prob.stf, 1, np.arange(prob.nshots), prob.survey(), obs)
+    with make_prop(Propagator, prob, max_batch=batch, with_adjoint=True) as P:
+        P.set_model(*prob.start)
+        r = P.gradient(cuda_shots(prob, ShotSpec), [obs[s] for s in range(prob.nshots)], want_syn=True)
+        assert abs(r["misfit"] - J) <= 2e-5 * abs(J)
+        assert rel_l2(r["glam"], gl) < TOL_GRAD
+        assert rel_l2(r["gmu"], gm) < TOL_GRAD
+        assert rel_l2(r["grho"], gd) < TOL_GRAD
+        assert rel_l2(np.stack(r["gstf"]), gs) < TOL_GRAD
+        # dead alignment rows and the PML carry no gradient
+        assert not np.any(r["glam"][prob.nz - prob.nPad:, :]) and not np.any(r["glam"][:prob.nPml, :])
+        # misfit-only path (cufd calc_id = 0) gives the same misfit
+        r0 = P.gradient(cuda_shots(prob, ShotSpec), [obs[s] for s in range(prob.nshots)], with_adj=False)
+        assert r0["misfit"] == r["misfit"]
+        # determinism: gathers instead of atomics => bit-identical reruns
+        r2 = P.gradient(cuda_shots(prob, ShotSpec), [obs[s] for s in range(prob.nshots)])
+        for k in ("glam", "gmu", "grho"):
+            assert np.array_equal(r[k], r2[k])
+
+
+def test_zero_residual_gives_zero_gradient():
+    _, Propagator, ShotSpec = _mods()
+    prob = problems.tiny()
+    with make_prop(Propagator, prob, max_batch=2, with_adjoint=True) as P:
+        P.set_model(*prob.true)
+        shots = cuda_shots(prob, ShotSpec)
+        obs = [o["ett"] for o in P.forward(shots, comps=("ett",))]
+        r = P.gradient(shots, obs)
+        assert r["misfit"] == 0.0 and not np.any(r["glam"]) and not np.any(r["gmu"]) and not np.any(r["grho"])
+
+
+@pytest.mark.parametrize("mk", [problems.tiny, problems.small])
+def test_against_committed_reference_golden(golden_dir, mk):
+    """Golden vectors = outputs of the reference's own CUDA path (tests/golden/make_cufd_golden.py)."""
+    _, Propagator, ShotSpec = _mods()
+    prob = mk()
+    path = os.path.join(golden_dir, "cufd_%s.npz" % prob.name)
+    if not os.path.exists(path):
+        pytest.skip("golden vectors not generated yet")
+    g = np.load(path)
+    with make_prop(Propagator, prob, max_batch=2, with_adjoint=True) as P:
+        P.set_model(*prob.true)
+        out = P.forward(cuda_shots(prob, ShotSpec))
+        for sid in range(prob.nshots):
+            for c in ("pr", "vx", "vz", "ett"):
+                assert rel_l2(out[sid][c], g["obs_%s%d" % (c, sid)]) < TOL_REF_TRACE
+        P.set_model(*prob.start)
+        r = P.gradient(cuda_shots(prob, ShotSpec), [g["obs_ett%d" % s] for s in range(prob.nshots)])
+        assert abs(r["misfit"] - float(g["misfit"])) <= 1e-4 * abs(float(g["misfit"]))
+        assert rel_l2(r["glam"], g["glam"]) < TOL_REF_GRAD
+        assert rel_l2(r["gmu"], g["gmu"]) < TOL_REF_GRAD
+        assert rel_l2(r["grho"], g["gden"]) < TOL_REF_GRAD
+        assert rel_l2(np.stack(r["gstf"]), g["gstf"]) < TOL_REF_GRAD
+
+
+def test_cufd_dropin_against_live_reference():
+    """sepfwi_cufd vs the reference's cufd compiled from /root/reference (oracle/_ref), same files,
+    same arguments, all three calc_id modes."""
+    import ctypes as C
+    from oracle import ref_cufd
+    from sepfwi import _lib, fwi_utils as ft
+    if not ref_cufd.available():
+        pytest.skip("oracle/_ref/libcufd_ref.so not present")
+    prob = problems.tiny()
+    ids = np.arange(prob.nshots, dtype=np.int32)
+    res = {}
+    for who in ("ref", "mine"):
+        work = tempfile.mkdtemp(prefix="dropin_" + who)
+        para, survey, data = os.path.join(work, "para.json"), os.path.join(work, "survey.json"), os.path.join(work, "d")
+        ft.paraGen(prob.nz, prob.nx, prob.dz, prob.dx, prob.nSteps, prob.dt, prob.f0, prob.nPml, prob.nPad, para, survey, data)
+        ft.surveyGen(prob.z_src, prob.x_src, prob.z_rec, prob.x_rec, survey)
+
+        def call(calc_id, model):
+            if who == "ref":
+                return ref_cufd.cufd(calc_id, *model, prob.stf, ids, para)
+            lam, mu, den = (np.ascontiguousarray(a, np.float32) for a in model)
+            stf = np.ascontiguousarray(prob.stf, np.float32)
+            J = np.zeros(1, np.float32)
+            g = [np.zeros_like(lam) for _ in range(3)]
+            gs = np.zeros_like(stf)
+            p = lambda a: a.ctypes.data
+            _lib.check(_lib.lib().sepfwi_cufd(p(J), p(g[0]), p(g[1]), p(g[2]), p(gs), p(lam), p(mu), p(den), p(stf),
+                                               calc_id, 0, ids.size, p(ids), para.encode()))
+            return float(J[0]), g[0], g[1], g[2], gs
+
+        call(2, prob.true)
+        obs = {c: [np.fromfile(os.path.join(data, "Shot_%s%d.bin" % (c, i)), np.float32) for i in ids]
+               for c in ("pr", "vx", "vz", "ett")}
+        res[who] = dict(obs=obs, grad=call(1, prob.start), J0=call(0, prob.start)[0])
+    for c in ("pr", "vx", "vz", "ett"):
+        for i in ids:
+            assert res["mine"]["obs"][c][i].shape == res["ref"]["obs"][c][i].shape
+            assert rel_l2(res["mine"]["obs"][c][i], res["ref"]["obs"][c][i]) < TOL_REF_TRACE
+    Jm, Jr = res["mine"]["grad"][0], res["ref"]["grad"][0]
+    assert abs(Jm - Jr) <= 1e-4 * abs(Jr) and abs(res["mine"]["J0"] - res["ref"]["J0"]) <= 1e-4 * abs(Jr)
+    for k in range(1, 5):
+        assert rel_l2(res["mine"]["grad"][k], res["ref"]["grad"][k]) < TOL_REF_GRAD, k
+    _lib.lib().sepfwi_cufd_clear_cache()
+
+
+def test_errors_are_reported_not_fatal():
+    from sepfwi._lib import SepfwiError
+    _, Propagator, ShotSpec = _mods()
+    prob = problems.tiny()
+    with make_prop(Propagator, prob) as P:
+        with pytest.raises(SepfwiError):                       # forward before set_model
+            P.forward(cuda_shots(prob, ShotSpec))
+        lam, mu, rho = prob.true
+        with pytest.raises(SepfwiError) as e:                  # CFL violation -> error code, not exit(1)
+            P2 = Propagator(prob.nz, prob.nx, prob.nPml, prob.nPad, prob.nSteps, prob.dz, prob.dx, 5e-3, prob.f0)
+            P2.set_model(lam, mu, rho)
+        assert e.value.code == -3
+        P.set_model(lam, mu, rho)
+        with pytest.raises(SepfwiError):                       # gradient on a handle without adjoint storage
+            P.gradient(cuda_shots(prob, ShotSpec), [np.zeros((len(prob.x_rec), prob.nSteps), np.float32)] * prob.nshots)
+    with pytest.raises(SepfwiError):
+        Propagator(10, 10, 2, 0, 5, 1.0, 1.0, 1e-3, 10.0)       # nPml < 4
