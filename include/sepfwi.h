@@ -70,7 +70,11 @@ typedef struct sepfwi_params {
     int   max_nrec;        /* upper bound of receivers per shot                                                        */
     int   with_adjoint;    /* 1: allocate boundary store + adjoint state (needed by sepfwi_gradient with_adj)          */
     int   kernels;         /* 0: default (fastest validated path), 1: force the unfused baseline kernels               */
-    int   reserved[6];
+    int   ref_race_compat; /* 0 (default): race-free adjoint source.  1: reproduce the reference's lost update in
+                              res_injection_exx/_ezz (utilities.cu:613-614,639-640, launched 32 receivers per block):
+                              when receiver 32k subtracts at the cell receiver 32k-1 adds to, the subtraction is dropped.
+                              Only for bit-level comparisons against the reference's own (racy) gradients.                 */
+    int   reserved[5];
 } sepfwi_params;
 
 typedef struct sepfwi_shot {
@@ -136,6 +140,16 @@ int sepfwi_ring_restore(sepfwi_handle *h, float *field, const float *bnd);
 int sepfwi_get_cpml(sepfwi_handle *h, int axis /*0=z,1=x*/, float *out6xN);
 long long sepfwi_launch_count(sepfwi_handle *h);
 int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
+
+/* Per-kernel device timing: with nsteps > 0 every launch of the first nsteps time steps of each
+ * time loop is bracketed by a CUDA-event pair on the launching stream; sepfwi_get_profile returns
+ * accumulated milliseconds and launch counts per kernel kind since the last sepfwi_set_profile. */
+enum { SEPFWI_K_RING_SAVE = 0, SEPFWI_K_STRESS_FWD, SEPFWI_K_VELOCITY_FWD, SEPFWI_K_RECORD, SEPFWI_K_VELOCITY_BWD,
+       SEPFWI_K_STRESS_BWD, SEPFWI_K_VELOCITY_ADJ, SEPFWI_K_INJECT, SEPFWI_K_STRESS_ADJ, SEPFWI_K_FUSED_FWD,
+       SEPFWI_K_FUSED_BWD, SEPFWI_NKERNEL };
+int sepfwi_set_profile(sepfwi_handle *h, int nsteps);
+int sepfwi_get_profile(sepfwi_handle *h, double *ms /*[SEPFWI_NKERNEL]*/, long long *count /*[SEPFWI_NKERNEL]*/);
+const char *sepfwi_kernel_name(int kind);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,11 @@ typedef struct {
     int fiber;         /* 0: horizontal fiber, exx  (recording_exx, SRC/utilities.cu:593-602)
                           1: vertical fiber,  ezz  (recording_ezz, SRC/utilities.cu:620-628) */
     float src_rxz;     /* sxx/szz ratio used by source_grad only (SRC/utilities.cu:719-730) */
+    int race;          /* emulate the reference's res_injection race (SRC/utilities.cu:613-614,
+                          launched <<<(nrec+31)/32, 32>>>): receivers r=32k-1 and r=32k sit in
+                          different thread blocks; when they touch the same cell both do a plain
+                          load-add-store and one update is lost.  0: race-free (sequential);
+                          1: the `+=` of the lower block is lost; 2: the `-=` of the upper block is lost */
 } ora_par;
 
 #define F(a, z, x) (a)[(size_t)(z) * nx + (x)]
@@ -694,8 +699,14 @@ double ora_gradient(const ora_par *p, const float *lam_mpa, const float *mu_mpa,
             for (int r = 0; r < nrec; r++) {
                 int z = zrec[r], x = xrec[r];
                 float rv = res[(size_t)r * nSteps + it];
-                if (p->fiber == 0) { F(a.vx, z, x) += rv; F(a.vx, z, x - 1) -= rv; }
-                else               { F(a.vz, z, x) += rv; F(a.vz, z - 1, x) -= rv; }
+                /* does the first receiver of the next block subtract at the cell this one adds to? */
+                int seam_hi = p->race && (r % 32 == 31) && r + 1 < nrec &&
+                              (p->fiber == 0 ? (zrec[r + 1] == z && xrec[r + 1] - 1 == x) : (xrec[r + 1] == x && zrec[r + 1] - 1 == z));
+                int seam_lo = p->race && (r % 32 == 0) && r > 0 &&
+                              (p->fiber == 0 ? (zrec[r - 1] == z && xrec[r - 1] == x - 1) : (xrec[r - 1] == x && zrec[r - 1] == z - 1));
+                int skip_add = seam_hi && p->race == 1, skip_sub = seam_lo && p->race == 2;
+                if (p->fiber == 0) { if (!skip_add) F(a.vx, z, x) += rv; if (!skip_sub) F(a.vx, z, x - 1) -= rv; }
+                else               { if (!skip_add) F(a.vz, z, x) += rv; if (!skip_sub) F(a.vz, z - 1, x) -= rv; }
             }
             stress_adj(p, &q.m, a.vz, a.vx, a.szz, a.sxx, a.sxz, a.ms_zz_z, a.ms_xz_x, a.ms_xz_z, a.ms_xx_x,
                        a.mv_z_z, a.mv_z_x, a.mv_x_z, a.mv_x_x);

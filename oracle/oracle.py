@@ -24,7 +24,7 @@ _LIB = None
 class OraPar(C.Structure):
     _fields_ = [("nz", C.c_int), ("nx", C.c_int), ("nPml", C.c_int), ("nPad", C.c_int),
                 ("nSteps", C.c_int), ("dz", C.c_float), ("dx", C.c_float), ("dt", C.c_float),
-                ("f0", C.c_float), ("mixed", C.c_int), ("fiber", C.c_int), ("src_rxz", C.c_float)]
+                ("f0", C.c_float), ("mixed", C.c_int), ("fiber", C.c_int), ("src_rxz", C.c_float), ("race", C.c_int)]
 
 
 def build():
@@ -56,8 +56,8 @@ def _d(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def make_par(nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, mixed=1, fiber=0, src_rxz=1.0):
-    return OraPar(nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, mixed, fiber, src_rxz)
+def make_par(nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, mixed=1, fiber=0, src_rxz=1.0, race=0):
+    return OraPar(nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, mixed, fiber, src_rxz, race)
 
 
 def shard_bounds(group_size, ngpu):

@@ -140,6 +140,8 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
     if (const JVal *dc = para.get("das_component")) if (dc->kind == JVal::Str && dc->str == "ezz") fiber = SEPFWI_FIBER_EZZ;
     double max_batch = 0;
     num("max_batch", max_batch);
+    int race_compat = 0;
+    if (const JVal *rc = para.get("ref_race_compat")) race_compat = (rc->kind == JVal::Bool && rc->b) || (rc->kind == JVal::Num && rc->num != 0);
 
     if (!read_first_line(sv->str, line)) return efail(SEPFWI_EIO, "Error opening survey file " + sv->str);
     JParser js{line.data(), line.data() + line.size()};
@@ -173,8 +175,8 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
 
     // handle cache
     char keybuf[512];
-    snprintf(keybuf, sizeof(keybuf), "%d|%d|%d|%d|%d|%d|%.9g|%.9g|%.9g|%.9g|%d|%d|%d", gpu_id, (int)nz, (int)nx, npml, (int)nPad, nS,
-             dz, dx, dt, f0, fiber, calc_id == 1, (int)max_batch);
+    snprintf(keybuf, sizeof(keybuf), "%d|%d|%d|%d|%d|%d|%.9g|%.9g|%.9g|%.9g|%d|%d|%d|%d", gpu_id, (int)nz, (int)nx, npml, (int)nPad, nS,
+             dz, dx, dt, f0, fiber, calc_id == 1, (int)max_batch, race_compat);
     std::unique_lock<std::mutex> lk(g_mu);
     std::unique_ptr<Cached> &slot = g_cache[keybuf];
     sepfwi_handle *h = slot ? slot->h : nullptr;
@@ -186,7 +188,7 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
         memset(&p, 0, sizeof(p));
         p.nz = (int)nz; p.nx = (int)nx; p.nPml = npml; p.nPad = (int)nPad; p.nSteps = nS;
         p.dz = (float)dz; p.dx = (float)dx; p.dt = (float)dt; p.f0 = (float)f0;
-        p.fiber = fiber; p.flavour = SEPFWI_FLAVOUR_CPML; p.max_nrec = maxrec; p.with_adjoint = calc_id == 1;
+        p.fiber = fiber; p.flavour = SEPFWI_FLAVOUR_CPML; p.max_nrec = maxrec; p.with_adjoint = calc_id == 1; p.ref_race_compat = race_compat;
         int B = (int)max_batch;
         if (B <= 0) {   // enough concurrent shots to give every launch a few million cells, within memory
             const double cells = (double)(p.nz - p.nPad) * p.nx;

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(BX *BY) k_velocity_fwd(const KArgs a)
     float dsxx_dx = dxf(sxx, i, d.c1x, d.c2x);
     if (!SPONGE) {
         const bool zp = (z < d.nPml) || (z > d.nzA - d.nPml - 1);
-        const bool xp = (x < d.nPml) || (x > d.nx - d.nPml - 1);   // one column wider than el_velocity.cu:56; a=0,K=1 there
+        const bool xp = (x < d.nPml) || (x > d.nx - d.nPml);       // el_velocity.cu:56,71: one column narrower than the stress kernel
         if (zp) {
             const float *c = a.cz + z;
             float *p0 = st + (S_FPSI + P_SZZ_Z) * d.fsz + i, *p1 = st + (S_FPSI + P_SXZ_Z) * d.fsz + i;

@@ -68,7 +68,55 @@ struct sepfwi_handle {
     cudaEvent_t ev[4];
     float fwd_ms = 0.f, bwd_ms = 0.f;
     static const int NBLK_RES = 64;
+    // per-kernel profile (sepfwi_set_profile): CUDA-event pairs around every launch of the first
+    // prof_steps time steps of each loop, on the launching stream
+    int prof_steps = 0;
+    struct ProfRec { int kind; cudaEvent_t e0, e1; };
+    std::vector<ProfRec> prof_recs;
+    double prof_ms[SEPFWI_NKERNEL] = {0};
+    long long prof_n[SEPFWI_NKERNEL] = {0};
 };
+
+static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
+                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_bwd"};
+
+// launch `stmt` and, in profile mode, bracket it with an event pair
+#define LAUNCH(h, KND, prof_on, st, stmt)                                     \
+    do {                                                                       \
+        if (prof_on) {                                                         \
+            sepfwi_handle::ProfRec r_; r_.kind = (KND);                        \
+            cudaEventCreate(&r_.e0); cudaEventCreate(&r_.e1);                  \
+            cudaEventRecord(r_.e0, st); stmt; cudaEventRecord(r_.e1, st);      \
+            (h)->prof_recs.push_back(r_);                                      \
+        } else { stmt; }                                                       \
+        (h)->launches++;                                                       \
+    } while (0)
+
+static void prof_collect(sepfwi_handle *h)
+{
+    for (auto &r : h->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { h->prof_ms[r.kind] += ms; h->prof_n[r.kind]++; }
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    h->prof_recs.clear();
+}
+
+extern "C" int sepfwi_set_profile(sepfwi_handle *h, int nsteps)
+{
+    if (!h) return fail(SEPFWI_EINVAL, "null handle");
+    h->prof_steps = nsteps > 0 ? nsteps : 0;
+    for (int k = 0; k < SEPFWI_NKERNEL; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
+    return 0;
+}
+extern "C" int sepfwi_get_profile(sepfwi_handle *h, double *ms, long long *count)
+{
+    if (!h || !ms || !count) return fail(SEPFWI_EINVAL, "null argument");
+    for (int k = 0; k < SEPFWI_NKERNEL; k++) { ms[k] = h->prof_ms[k]; count[k] = h->prof_n[k]; }
+    return 0;
+}
+extern "C" const char *sepfwi_kernel_name(int k) { return k >= 0 && k < SEPFWI_NKERNEL ? k_names[k] : ""; }
+
 
 extern "C" const char *sepfwi_last_error(void) { return g_err; }
 // used by the other translation units of the library to report through the same channel
@@ -87,7 +135,7 @@ static void build_cpml(int N, int nPml, float dh, float f0, float dt, std::vecto
     const float alpha_max = (float)(2.0 * PI * (f0 / 2.0));
     const float npower = 8.0f, kmax = 2.0f, w1 = 0.25f, w2 = 0.75f;
     const float thick = nPml * dh;
-    const float d0 = (float)(-(npower + 1) * 3000.0f * log(0.0008f) / (2.0 * thick));
+    const float d0 = (float)(-(npower + 1) * 3000.0f * log((double)0.0008f) / (2.0 * thick));
     auto prof = [&](float depth, float &damp, float &K, float &alpha) {
         if (depth >= 0.0f) {
             const float dn = depth / thick;
@@ -412,8 +460,13 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
                 const int z = sh.zrec[r], x = sh.xrec[r];
                 const float *w = h->h_flt + h->o_w + ((size_t)s * d.maxRec + r) * 3;
                 const int c = z * d.ldx + x;
-                if (w[0] != 0.f) { v.push_back({F_VX, c, r, w[0]}); v.push_back({F_VX, c - 1, r, -w[0]}); }
-                if (w[1] != 0.f) { v.push_back({F_VZ, c, r, w[1]}); v.push_back({F_VZ, c - d.ldx, r, -w[1]}); }
+                // reference-race compatibility: first receiver of a 32-receiver block whose `-=` lands on the
+                // cell the previous receiver (last thread of the previous block) adds to loses that update
+                const bool seam = h->p.ref_race_compat && r > 0 && (r % 32) == 0;
+                const bool drop_x = seam && sh.zrec[r - 1] == z && sh.xrec[r - 1] == x - 1;
+                const bool drop_z = seam && sh.xrec[r - 1] == x && sh.zrec[r - 1] == z - 1;
+                if (w[0] != 0.f) { v.push_back({F_VX, c, r, w[0]}); if (!drop_x) v.push_back({F_VX, c - 1, r, -w[0]}); }
+                if (w[1] != 0.f) { v.push_back({F_VZ, c, r, w[1]}); if (!drop_z) v.push_back({F_VZ, c - d.ldx, r, -w[1]}); }
                 if (w[2] != 0.f) {
                     v.push_back({F_VX, c + d.ldx, r, 0.5f * w[2]}); v.push_back({F_VX, c, r, -0.5f * w[2]});
                     v.push_back({F_VZ, c + 1, r, 0.5f * w[2]});     v.push_back({F_VZ, c, r, -0.5f * w[2]});
@@ -462,18 +515,18 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
     CU(cudaEventRecord(h->ev[0], st));
     if (!h->sponge) {
         for (int it = 0; it <= d.nSteps - 2; it++) {
-            if (save_ring) { k_ring_save<<<ringgrd, 256, 0, st>>>(a, it); h->launches++; }
-            k_stress_fwd<false><<<grd, blk, 0, st>>>(a, it);
-            k_velocity_fwd<false><<<grd, blk, 0, st>>>(a);
-            h->launches += 2;
-            if (mrec > 0) { k_record<false><<<rgrd, 128, 0, st>>>(a, it + 1, mask, h->p.fiber); h->launches++; }
+            const bool pr = it < h->prof_steps;
+            if (save_ring) LAUNCH(h, SEPFWI_K_RING_SAVE, pr, st, (k_ring_save<<<ringgrd, 256, 0, st>>>(a, it)));
+            LAUNCH(h, SEPFWI_K_STRESS_FWD, pr, st, (k_stress_fwd<false><<<grd, blk, 0, st>>>(a, it)));
+            LAUNCH(h, SEPFWI_K_VELOCITY_FWD, pr, st, (k_velocity_fwd<false><<<grd, blk, 0, st>>>(a)));
+            if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, it + 1, mask, h->p.fiber)));
         }
     } else {
         for (int it = 0; it < d.nSteps; it++) {
-            k_velocity_fwd<true><<<grd, blk, 0, st>>>(a);
-            k_stress_fwd<true><<<grd, blk, 0, st>>>(a, it);
-            h->launches += 2;
-            if (mrec > 0) { k_record<true><<<rgrd, 128, 0, st>>>(a, it, mask, h->p.fiber); h->launches++; }
+            const bool pr = it < h->prof_steps;
+            LAUNCH(h, SEPFWI_K_VELOCITY_FWD, pr, st, (k_velocity_fwd<true><<<grd, blk, 0, st>>>(a)));
+            LAUNCH(h, SEPFWI_K_STRESS_FWD, pr, st, (k_stress_fwd<true><<<grd, blk, 0, st>>>(a, it)));
+            if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<true><<<rgrd, 128, 0, st>>>(a, it, mask, h->p.fiber)));
         }
     }
     CU(cudaEventRecord(h->ev[1], st));
@@ -510,6 +563,7 @@ extern "C" int sepfwi_forward(sepfwi_handle *h, int nshots, const sepfwi_shot *s
                     CU(cudaMemcpyAsync(shots[s0 + s].out[c], h->trace + ((size_t)s * d.nTrace + c) * d.maxRec * d.nSteps,
                                        (size_t)shots[s0 + s].nrec * d.nSteps * sizeof(float), kind, st));
         CU(cudaStreamSynchronize(st));
+        prof_collect(h);
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
         h->fwd_ms += ms;
@@ -533,12 +587,12 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     dim3 igrd((minj + 127) / 128, nb);
     CU(cudaEventRecord(h->ev[2], st));
     for (int it = d.nSteps - 2; it >= 0; it--) {
-        k_velocity_bwd<<<rgrd, blk, 0, st>>>(a, it);
-        k_stress_bwd<<<rgrd, blk, 0, st>>>(a, it);
-        k_velocity_adj<<<grd, blk, 0, st>>>(a);
-        if (minj > 0) { k_inject<<<igrd, 128, 0, st>>>(a, it); h->launches++; }
-        k_stress_adj<<<grd, blk, 0, st>>>(a);
-        h->launches += 4;
+        const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
+        LAUNCH(h, SEPFWI_K_VELOCITY_BWD, pr, st, (k_velocity_bwd<<<rgrd, blk, 0, st>>>(a, it)));
+        LAUNCH(h, SEPFWI_K_STRESS_BWD, pr, st, (k_stress_bwd<<<rgrd, blk, 0, st>>>(a, it)));
+        LAUNCH(h, SEPFWI_K_VELOCITY_ADJ, pr, st, (k_velocity_adj<<<grd, blk, 0, st>>>(a)));
+        if (minj > 0) LAUNCH(h, SEPFWI_K_INJECT, pr, st, (k_inject<<<igrd, 128, 0, st>>>(a, it)));
+        LAUNCH(h, SEPFWI_K_STRESS_ADJ, pr, st, (k_stress_adj<<<grd, blk, 0, st>>>(a)));
     }
     CU(cudaEventRecord(h->ev[3], st));
     CU(cudaGetLastError());
@@ -595,6 +649,7 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
             if (rc) return rc;
         }
         CU(cudaStreamSynchronize(st));
+        prof_collect(h);
         for (int s = 0; s < nb; s++) J += hj[s];
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));

@@ -21,7 +21,8 @@ class Params(C.Structure):
     _fields_ = [("nz", C.c_int), ("nx", C.c_int), ("nPml", C.c_int), ("nPad", C.c_int), ("nSteps", C.c_int),
                 ("dz", C.c_float), ("dx", C.c_float), ("dt", C.c_float), ("f0", C.c_float),
                 ("fiber", C.c_int), ("flavour", C.c_int), ("max_batch", C.c_int), ("max_nrec", C.c_int),
-                ("with_adjoint", C.c_int), ("kernels", C.c_int), ("reserved", C.c_int * 6)]
+                ("with_adjoint", C.c_int), ("kernels", C.c_int), ("ref_race_compat", C.c_int),
+                ("reserved", C.c_int * 5)]
 
 
 class Shot(C.Structure):
@@ -35,7 +36,9 @@ class Shot(C.Structure):
 SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destroy", "sepfwi_set_model",
            "sepfwi_courant", "sepfwi_forward", "sepfwi_gradient", "sepfwi_cufd", "sepfwi_cufd_clear_cache",
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
-           "sepfwi_launch_count", "sepfwi_last_timing"]
+           "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
+           "sepfwi_kernel_name"]
+NKERNEL = 11
 
 _lib = None
 
@@ -71,6 +74,10 @@ def lib():
         L.sepfwi_get_cpml.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sepfwi_launch_count.argtypes = [C.c_void_p]
         L.sepfwi_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.sepfwi_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.sepfwi_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+        L.sepfwi_kernel_name.argtypes = [C.c_int]
+        L.sepfwi_kernel_name.restype = C.c_char_p
         _lib = L
     return _lib
 

@@ -55,10 +55,11 @@ class ShotSpec(object):
 
 class Propagator(object):
     def __init__(self, nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, fiber=_lib.FIBER_EXX,
-                 flavour=_lib.FLAVOUR_CPML, max_batch=1, max_nrec=1, with_adjoint=False, device=0, kernels=0):
+                 flavour=_lib.FLAVOUR_CPML, max_batch=1, max_nrec=1, with_adjoint=False, device=0, kernels=0,
+                 ref_race_compat=False):
         self.params = Params(int(nz), int(nx), int(nPml), int(nPad), int(nSteps), float(dz), float(dx), float(dt),
                              float(f0), int(fiber), int(flavour), int(max_batch), int(max_nrec),
-                             1 if with_adjoint else 0, int(kernels))
+                             1 if with_adjoint else 0, int(kernels), 1 if ref_race_compat else 0)
         self.device = int(device)
         self.nz, self.nx, self.nSteps = int(nz), int(nx), int(nSteps)
         self._h = C.c_void_p()
@@ -140,6 +141,17 @@ class Propagator(object):
         f, b = C.c_float(), C.c_float()
         check(lib().sepfwi_last_timing(self._h, C.byref(f), C.byref(b)))
         return f.value, b.value
+
+    def set_profile(self, nsteps):
+        """Bracket every launch of the first `nsteps` steps of each time loop with CUDA events."""
+        check(lib().sepfwi_set_profile(self._h, int(nsteps)))
+
+    def profile(self):
+        """{kernel name: (total ms, launches)} accumulated since set_profile."""
+        ms = (C.c_double * _lib.NKERNEL)()
+        n = (C.c_longlong * _lib.NKERNEL)()
+        check(lib().sepfwi_get_profile(self._h, ms, n))
+        return {lib().sepfwi_kernel_name(k).decode(): (ms[k], int(n[k])) for k in range(_lib.NKERNEL) if n[k] > 0}
 
     def ring_len(self):
         return int(lib().sepfwi_ring_len(C.byref(self.params)))

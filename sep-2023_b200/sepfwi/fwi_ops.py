@@ -1,0 +1,232 @@
+"""Drop-in for the reference's pybind module `fwi` (DAS_Waveform_Inversion/Ops/FWI/Src/Torch_Fwi.cpp):
+
+    forward (Lambda, Mu, Den, Stf, gpu_id, Shot_ids, para_fname) -> [misfit]                       (:12-36)
+    backward(Lambda, Mu, Den, Stf, ngpu,   Shot_ids, para_fname) -> [misfit, gLam, gMu, gDen, gStf] (:38-104)
+    obscalc (Lambda, Mu, Den, Stf, ngpu,   Shot_ids, para_fname) -> None, writes Shot_*.bin        (:106-136)
+
+Same argument meaning: Lambda/Mu in MPa and Den in kg/m^3 as (nz_pad, nx_pad) float32 tensors, Stf
+(nSrc, nSteps), Shot_ids int32, para_fname the para_file.json written by fwi_utils.paraGen.  Differences,
+all deliberate and documented in INTEGRATION.md:
+  * tensors may live on the GPU (the reference only takes CPU tensors); results come back on the inputs' device;
+  * errors raise RuntimeError instead of exit(1);
+  * `ngpu` > 1 in one process drives GPUs 0..ngpu-1 from threads like the reference's OpenMP loop; under
+    torch.distributed (one process per GPU) the shots are sharded over the ranks instead and the partial
+    gradients are summed by a single NCCL all-reduce (sepfwi.dist);
+  * gStf has the row of EVERY processed shot at its shot id (the reference keeps GPU 0's rows at local
+    indices only, Torch_Fwi.cpp:103 / libCUFD.cu:671-673).
+Handles, CPML tables and observed data are cached between calls (the reference rebuilds them per call).
+"""
+import os
+import threading
+
+import numpy as np
+
+from . import _lib, dist, fwi_utils
+from .engine import Propagator, ShotSpec
+
+_PROPS = {}
+_OBS = {}
+_LOCK = threading.Lock()
+
+
+def clear_cache():
+    with _LOCK:
+        for p in _PROPS.values():
+            p.close()
+        _PROPS.clear()
+        _OBS.clear()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def auto_batch(nz, nx, nPad, nSteps, nrec, nPml, with_adjoint, nshots, device):
+    """Concurrent shots per launch: enough to give every launch a few million cells, within memory."""
+    torch = _torch()
+    cells = float((nz - nPad) * nx)
+    B = min(16, int(4.0e6 / cells) + 1)
+    ring = 10.0 * ((nz - nPad - 2 * nPml + 4) + (nx - 2 * nPml + 4))
+    per = (5.0 * ring * nSteps * 4 + 29.0 * cells * 4 if with_adjoint else 13.0 * cells * 4) + 4.0 * nrec * nSteps * 4
+    free = torch.cuda.mem_get_info(device)[0]
+    while B > 1 and per * B > 0.6 * free:
+        B -= 1
+    return max(1, min(B, nshots))
+
+
+def _prop(para, device, with_adjoint, nrec, nshots):
+    fiber = _lib.FIBER_EZZ if para.get("das_component", "exx") == "ezz" else _lib.FIBER_EXX
+    B = int(para.get("max_batch", 0)) or auto_batch(para["nz"], para["nx"], para["nPad"], para["nSteps"], nrec,
+                                                    para["nPoints_pml"], with_adjoint, nshots, device)
+    key = (device, para["nz"], para["nx"], para["nPoints_pml"], para["nPad"], para["nSteps"], float(para["dz"]),
+           float(para["dx"]), float(para["dt"]), float(para["f0"]), fiber, bool(with_adjoint))
+    with _LOCK:
+        p = _PROPS.get(key)
+        if p is not None and (p.params.max_nrec < nrec or p.params.max_batch < min(B, nshots)):
+            p.close()
+            p = None
+        if p is None:
+            p = Propagator(para["nz"], para["nx"], para["nPoints_pml"], para["nPad"], para["nSteps"], para["dz"],
+                           para["dx"], para["dt"], para["f0"], fiber=fiber, max_batch=B, max_nrec=nrec,
+                           with_adjoint=with_adjoint, device=device)
+            _PROPS[key] = p
+    return p
+
+
+def _shots(para, shot_ids, Stf):
+    torch = _torch()
+    stf = Stf.detach().cpu().numpy() if isinstance(Stf, torch.Tensor) else np.asarray(Stf)
+    stf = np.ascontiguousarray(stf, np.float32)
+    sv = fwi_utils.load_survey(para["survey_fname"], shot_ids, para["nPoints_pml"])
+    return [ShotSpec(s["zs"], s["xs"], s["zrec"], s["xrec"], stf[int(sid)], s["src_rxz"])
+            for s, sid in zip(sv, shot_ids)], stf.shape
+
+
+def _obs(para, sid, nrec, device):
+    """Shot_ett{id}.bin (libCUFD.cu:221-223), cached on the device keyed by path + mtime + size."""
+    torch = _torch()
+    path = os.path.join(para["data_dir_name"], "Shot_ett%d.bin" % int(sid))
+    try:
+        st = os.stat(path)
+    except OSError:
+        raise RuntimeError("File reading error! Attempted to read %s" % path)
+    key = (path, st.st_mtime_ns, st.st_size, device)
+    t = _OBS.get(key)
+    if t is None:
+        a = np.fromfile(path, np.float32)
+        if a.size != nrec * para["nSteps"]:
+            raise RuntimeError("%s holds %d floats, expected %d x %d" % (path, a.size, nrec, para["nSteps"]))
+        t = torch.from_numpy(a.reshape(nrec, para["nSteps"])).to("cuda:%d" % device)
+        _OBS[key] = t
+    return t
+
+
+def _ids(Shot_ids):
+    torch = _torch()
+    if isinstance(Shot_ids, torch.Tensor):
+        return [int(v) for v in Shot_ids.detach().cpu().reshape(-1).tolist()]
+    return [int(v) for v in np.asarray(Shot_ids).reshape(-1).tolist()]
+
+
+def _dev_of(t, default=None):
+    torch = _torch()
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        return t.device.index
+    if default is not None:
+        return default
+    if not torch.cuda.is_available():
+        raise RuntimeError("sepfwi needs a CUDA device; there is no CPU fallback")
+    return torch.cuda.current_device()
+
+
+def _model_on(device, *tensors):
+    torch = _torch()
+    out = []
+    for t in tensors:
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t))
+        out.append(t.detach().to(device="cuda:%d" % device, dtype=torch.float32).contiguous())
+    return out
+
+
+def _gradient_on_device(device, Lambda, Mu, Den, Stf, ids, para, with_adj):
+    """Misfit (+gradients) of shots `ids` on one GPU.  Returns (misfit, gl, gm, gd, gstf_full) with CUDA tensors."""
+    torch = _torch()
+    with torch.cuda.device(device):
+        shots, stf_shape = _shots(para, ids, Stf)
+        nrec = max([s.nrec for s in shots] + [1])
+        P = _prop(para, device, with_adj, nrec, len(ids))
+        lam, mu, den = _model_on(device, Lambda, Mu, Den)
+        P.set_model(lam, mu, den)
+        obs = [_obs(para, sid, s.nrec, device) for sid, s in zip(ids, shots)]
+        r = P.gradient(shots, obs, with_adj=with_adj, device=True)
+        gstf = torch.zeros(stf_shape, dtype=torch.float32, device="cuda:%d" % device)
+        if with_adj:
+            for sid, g in zip(ids, r["gstf"]):
+                gstf[sid] = torch.from_numpy(g).to(gstf.device)
+        return r["misfit"], r["glam"], r["gmu"], r["grho"], gstf
+
+
+def forward(Lambda, Mu, Den, Stf, gpu_id, Shot_ids, para_fname):
+    """Misfit only (cufd calc_id = 0) on GPU `gpu_id`."""
+    torch = _torch()
+    para = fwi_utils.read_json_first_line(para_fname)
+    J = _gradient_on_device(int(gpu_id), Lambda, Mu, Den, Stf, _ids(Shot_ids), para, False)[0]
+    return [torch.tensor([J], dtype=torch.float32)]
+
+
+def backward(Lambda, Mu, Den, Stf, ngpu, Shot_ids, para_fname):
+    torch = _torch()
+    para = fwi_utils.read_json_first_line(para_fname)
+    ids = _ids(Shot_ids)
+    out_dev = Lambda.device if isinstance(Lambda, torch.Tensor) else torch.device("cpu")
+    if dist.is_distributed():
+        ws, rank = dist.world()
+        dev = _dev_of(Lambda)
+        J, gl, gm, gd, gs = _gradient_on_device(dev, Lambda, Mu, Den, Stf, dist.shard(ids, ws, rank), para, True)
+        J, gl, gm, gd, gs = dist.allreduce_gradients(J, gl, gm, gd, gs)
+    elif int(ngpu) <= 1:
+        J, gl, gm, gd, gs = _gradient_on_device(_dev_of(Lambda), Lambda, Mu, Den, Stf, ids, para, True)
+    else:
+        ngpu = int(ngpu)
+        if ngpu > len(ids):
+            raise RuntimeError("The number of GPUs should be smaller than the number of shots!")
+        if ngpu > torch.cuda.device_count():
+            raise RuntimeError("ngpu=%d but only %d CUDA devices are visible" % (ngpu, torch.cuda.device_count()))
+        res = [None] * ngpu
+        err = []
+
+        def work(i):
+            try:
+                res[i] = _gradient_on_device(i, Lambda, Mu, Den, Stf, dist.shard(ids, ngpu, i), para, True)
+            except Exception as e:   # surfaced below: a failing GPU must not be silent
+                err.append(e)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(ngpu)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if err:
+            raise err[0]
+        J = sum(r[0] for r in res)
+        gl, gm, gd, gs = (sum(r[k].to("cuda:0") for r in res) for k in range(1, 5))
+    return [torch.tensor([J], dtype=torch.float32).to(out_dev), gl.to(out_dev), gm.to(out_dev), gd.to(out_dev),
+            gs.to(out_dev)]
+
+
+def obscalc(Lambda, Mu, Den, Stf, ngpu, Shot_ids, para_fname):
+    """Forward-model the shots and write Shot_{pr,vx,vz,ett}{id}.bin into data_dir_name (libCUFD.cu:755-769)."""
+    torch = _torch()
+    para = fwi_utils.read_json_first_line(para_fname)
+    ids = _ids(Shot_ids)
+    if dist.is_distributed():
+        ws, rank = dist.world()
+        groups = [(_dev_of(Lambda), dist.shard(ids, ws, rank))]
+    elif int(ngpu) <= 1:
+        groups = [(_dev_of(Lambda), ids)]
+    else:
+        if int(ngpu) > len(ids):
+            raise RuntimeError("The number of GPUs should be smaller than the number of shots!")
+        groups = [(i, dist.shard(ids, int(ngpu), i)) for i in range(int(ngpu))]
+    os.makedirs(para["data_dir_name"], exist_ok=True)
+    err = []
+
+    def work(dev, sub):
+        try:
+            with torch.cuda.device(dev):
+                shots, _ = _shots(para, sub, Stf)
+                nrec = max([s.nrec for s in shots] + [1])
+                P = _prop(para, dev, False, nrec, len(sub))
+                P.set_model(*_model_on(dev, Lambda, Mu, Den))
+                out = P.forward(shots)
+                for sid, o in zip(sub, out):
+                    for c in ("pr", "vx", "vz", "ett"):
+                        o[c].tofile(os.path.join(para["data_dir_name"], "Shot_%s%d.bin" % (c, sid)))
+        except Exception as e:
+            err.append(e)
+
+    th = [threading.Thread(target=work, args=g) for g in groups]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if err:
+        raise err[0]

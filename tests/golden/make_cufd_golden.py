@@ -50,5 +50,5 @@ def run(prob, outdir):
 if __name__ == "__main__":
     out = os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(out, exist_ok=True)
-    for prob in (problems.tiny(), problems.small()):
+    for prob in (problems.tiny(), problems.small(), problems.small_adj()):
         run(prob, out)

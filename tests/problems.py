@@ -95,15 +95,24 @@ def tiny(fiber=0):
                    [2, 3], [14, 40], z_rec, x_rec, fiber)
 
 
-def small():
-    """64 x 96 interior, nPml 16, 3 shots, 40 adjacent receivers (adjacent channels exercise the
-    residual-injection overlap the reference races on), 420 steps."""
+def small(adjacent=False):
+    """64 x 96 interior, nPml 16, 3 shots, 40 receivers, 420 steps.
+    adjacent=False: receivers two cells apart, no two receivers touch the same cell.
+    adjacent=True ("small_adj"): 40 ADJACENT receivers.  Receivers 31 and 32 then sit in different
+    32-thread blocks of the reference's res_injection_exx launch and both update cell x_31 with a plain
+    load-add-store (Src/utilities.cu:613-614): the reference loses one update there on every time step,
+    which changes its gradient by ~15%.  The oracle reproduces that with par.race = 2."""
     rng = np.random.default_rng(7)
     nz, nx = 64, 96
     vt = layered_vp(nz, nx, 1700.0, 3600.0, 5, rng, nlens=10, lens_amp=0.1, sigma=(3, 10))
     vs = smooth(vt, 6)
-    return Problem("small", nz, nx, 16, 10.0, 10.0, 1.0e-3, 420, 15.0, vt, vs,
-                   [1, 1, 2], [10, 48, 86], np.full(40, 50), np.arange(28, 68), 0)
+    x_rec = np.arange(28, 68) if adjacent else np.arange(8, 88, 2)
+    return Problem("small_adj" if adjacent else "small", nz, nx, 16, 10.0, 10.0, 1.0e-3, 420, 15.0, vt, vs,
+                   [1, 1, 2], [10, 48, 86], np.full(40, 50), x_rec, 0)
+
+
+def small_adj():
+    return small(adjacent=True)
 
 
 def reference_test(nSteps=1501, nshots=19):

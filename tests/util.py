@@ -9,9 +9,9 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / n) if n > 0 else float(np.linalg.norm(a))
 
 
-def oracle_par(O, prob, mixed=1):
+def oracle_par(O, prob, mixed=1, race=0):
     return O.make_par(prob.nz, prob.nx, prob.nPml, prob.nPad, prob.nSteps, prob.dz, prob.dx, prob.dt, prob.f0,
-                      mixed=mixed, fiber=prob.fiber)
+                      mixed=mixed, fiber=prob.fiber, race=race)
 
 
 def oracle_observed(O, prob, comps=("ett",)):
