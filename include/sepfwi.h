@@ -146,7 +146,7 @@ int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
  * accumulated milliseconds and launch counts per kernel kind since the last sepfwi_set_profile. */
 enum { SEPFWI_K_RING_SAVE = 0, SEPFWI_K_STRESS_FWD, SEPFWI_K_VELOCITY_FWD, SEPFWI_K_RECORD, SEPFWI_K_VELOCITY_BWD,
        SEPFWI_K_STRESS_BWD, SEPFWI_K_VELOCITY_ADJ, SEPFWI_K_INJECT, SEPFWI_K_STRESS_ADJ, SEPFWI_K_FUSED_FWD,
-       SEPFWI_K_FUSED_BWD, SEPFWI_NKERNEL };
+       SEPFWI_K_FUSED_RECON, SEPFWI_K_FUSED_ADJ, SEPFWI_NKERNEL };
 int sepfwi_set_profile(sepfwi_handle *h, int nsteps);
 int sepfwi_get_profile(sepfwi_handle *h, double *ms /*[SEPFWI_NKERNEL]*/, long long *count /*[SEPFWI_NKERNEL]*/);
 const char *sepfwi_kernel_name(int kind);

@@ -23,7 +23,15 @@ enum { F_SZZ = 0, F_SXZ = 1, F_SXX = 2, F_VZ = 3, F_VX = 4, NFIELD = 5 };
 //   the adjoint sweep reuses the same slots for its own memory variables
 //   (el_stress_adj.cu / el_velocity_adj.cu use the forward arrays, libCUFD.cu:503-517).
 enum { P_VZ_Z = 0, P_VZ_X = 1, P_VX_Z = 2, P_VX_X = 3, P_SZZ_Z = 4, P_SXZ_X = 5, P_SXZ_Z = 6, P_SXX_X = 7, NPSI = 8 };
-enum { S_FWD = 0, S_FPSI = NFIELD, S_ADJ = NFIELD + NPSI, S_APSI = 2 * NFIELD + NPSI, NSTATE = 2 * (NFIELD + NPSI) };
+// State block of one slot (array index; every array has fsz floats):
+//   S_FWD / S_FWD1    forward fields, ping-pong pair (the baseline kernels update S_FWD in place)
+//   S_FPSI            forward CPML memory: P_V* (stress update) and P_S* (velocity update)
+//   S_FPSIV1          second copy of the four P_V* for the fused kernel's out-of-place update
+//   S_ADJ / S_ADJ1    adjoint fields, ping-pong pair
+//   S_APSI / S_APSI1  adjoint CPML memory, ping-pong pair
+enum { S_FWD = 0, S_FWD1 = NFIELD, S_FPSI = 2 * NFIELD, S_FPSIV1 = 2 * NFIELD + NPSI, NSTATE_FWD = 2 * NFIELD + NPSI + 4,
+       S_ADJ = NSTATE_FWD, S_ADJ1 = S_ADJ + NFIELD, S_APSI = S_ADJ + 2 * NFIELD, S_APSI1 = S_APSI + NPSI,
+       NSTATE = S_APSI1 + NPSI };
 enum { M_LAM = 0, M_MU = 1, M_MUAVE = 2, M_BYCA = 3, M_BYCB = 4, NMODEL = 5 };
 // 1-D CPML profiles, stored as six rows: 1/K, a, b at integer points then at half points
 enum { C_RK = 0, C_A = 1, C_B = 2, C_RKH = 3, C_AH = 4, C_BH = 5, NCOEF = 6 };
@@ -65,6 +73,12 @@ struct SlotTab {
     const int *injRec;         // [slot][maxCon]
     const float *injCoef;      // [slot][maxCon]
     int maxInj, maxCon;
+    // receivers bucketed by the fused kernels' tiles (CSR): tilePtr[slot][nTiles+1], tileRec[slot][maxRec]
+    const int *tilePtr, *tileRec;
+    int nTiles, ntx;
+    // injection targets bucketed by tile INCLUDING its 2-cell halo (a target may sit in up to 4 tiles):
+    // tileInjPtr[slot][nTiles+1], tileInj[slot][4*maxInj] -> index into injCell/injField/injPtr
+    const int *tileInjPtr, *tileInj;
 };
 
 struct KArgs {
@@ -111,6 +125,25 @@ __device__ __forceinline__ int ring_indices(const Dims &d, int z, int x, int idx
         if (ib >= 0 && ib < L) idx[n++] = L * (2 * d.nzB + d.nxB) + ib * d.nxB + j; // bottom
     }
     return n;
+}
+
+// register-only variant: a cell sits in at most one side strip and one top/bottom strip (interior >= 8 cells);
+// i0 / i1 = ring index or -1
+__device__ __forceinline__ void ring_indices2(const Dims &d, int z, int x, int &i0, int &i1)
+{
+    const int L = 5;
+    i0 = -1; i1 = -1;
+    const int i = z - (d.nPml - 2), j = x - (d.nPml - 2);
+    if (i >= 0 && i < d.nzB) {
+        const int jr = d.nx - d.nPml + 1 - x;
+        if (j >= 0 && j < L) i0 = j * d.nzB + i;
+        else if (jr >= 0 && jr < L) i0 = L * d.nzB + jr * d.nzB + i;
+    }
+    if (j >= 0 && j < d.nxB) {
+        const int ib = d.nzA - d.nPml + 1 - z;
+        if (i >= 0 && i < L) i1 = 2 * L * d.nzB + i * d.nxB + j;
+        else if (ib >= 0 && ib < L) i1 = L * (2 * d.nzB + d.nxB) + ib * d.nxB + j;
+    }
 }
 
 }  // namespace sepfwi

@@ -161,7 +161,7 @@ __global__ void k_ring_copy_field(const Dims d, float *field, float *bnd, const 
 // Trace recording at sample `samp`.  recording / _vx / _vz / _exx / _ezz, utilities.cu:593-703.
 // SPONGE flavour: elasticSolver.py:263-276 (pr halved, strain rates divided by the spacing).
 template <bool SPONGE>
-__global__ void k_record(const KArgs a, const int samp, const int mask, const int fiber)
+__global__ void k_record(const KArgs a, const int samp, const int mask, const int fiber, const int par)
 {
     const Dims &d = a.d;
     const int r = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
@@ -169,9 +169,9 @@ __global__ void k_record(const KArgs a, const int samp, const int mask, const in
     const int z = a.t.zrec[(size_t)s * d.maxRec + r], x = a.t.xrec[(size_t)s * d.maxRec + r];
     const int ld = d.ldx;
     const size_t i = (size_t)z * ld + x;
-    const float *st = slot_state(a, s);
-    const float *vz = st + (S_FWD + F_VZ) * d.fsz, *vx = st + (S_FWD + F_VX) * d.fsz;
-    const float *szz = st + (S_FWD + F_SZZ) * d.fsz, *sxx = st + (S_FWD + F_SXX) * d.fsz;
+    const float *st = slot_state(a, s) + (size_t)(par ? S_FWD1 : S_FWD) * d.fsz;   // par: which ping-pong buffer holds the state
+    const float *vz = st + F_VZ * d.fsz, *vx = st + F_VX * d.fsz;
+    const float *szz = st + F_SZZ * d.fsz, *sxx = st + F_SXX * d.fsz;
     float *tr = a.trace + (size_t)s * d.nTrace * d.maxRec * d.nSteps + (size_t)r * d.nSteps + samp;
     const size_t cs = (size_t)d.maxRec * d.nSteps;
     float exx = vx[i] - vx[i - 1];

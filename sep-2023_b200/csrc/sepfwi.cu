@@ -17,6 +17,8 @@
 #include "../../include/sepfwi.h"
 #include "common.cuh"
 #include "kernels_base.cuh"
+#include "kernels_fused.cuh"
+#include "kernels_fused_bwd.cuh"
 
 using namespace sepfwi;
 
@@ -57,7 +59,9 @@ struct sepfwi_handle {
     size_t n_int = 0, n_flt = 0;
     SlotTab tab;
     // offsets (in elements) of the packed tables
-    size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec;
+    size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_tilePtr, o_tileRec, o_tileInjPtr, o_tileInj;
+    int ntx = 0, ntz = 0;
+    bool fused = false;
     size_t o_amp, o_rxz, o_w, o_injCoef;
     bool use_w = false;
     // host copies
@@ -78,7 +82,7 @@ struct sepfwi_handle {
 };
 
 static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
-                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_bwd"};
+                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_recon", "fused_adj"};
 
 // launch `stmt` and, in profile mode, bracket it with an event pair
 #define LAUNCH(h, KND, prof_on, st, stmt)                                     \
@@ -273,7 +277,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
             return c;                                                                                    \
         }                                                                                                \
     } while (0)
-    h->d.sstride = (size_t)(pp->with_adjoint ? NSTATE : (NFIELD + NPSI)) * d.fsz;
+    h->d.sstride = (size_t)(pp->with_adjoint ? NSTATE : NSTATE_FWD) * d.fsz;
     ALLOC(h->state, (size_t)B * d.sstride * sizeof(float));
     ALLOC(h->model, (size_t)NMODEL * d.fsz * sizeof(float));
     ALLOC(h->cz, (size_t)NCOEF * d.nzA * sizeof(float));
@@ -299,7 +303,16 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     h->o_zrec = takei((size_t)B * d.maxRec); h->o_xrec = takei((size_t)B * d.maxRec);
     h->o_injN = takei(B); h->o_injCell = takei((size_t)B * maxInj); h->o_injField = takei((size_t)B * maxInj);
     h->o_injPtr = takei((size_t)B * (maxInj + 1)); h->o_injRec = takei((size_t)B * maxCon);
+    h->ntx = (d.nx + FTX - 1) / FTX; h->ntz = (d.nzA + FTZ - 1) / FTZ;
+    h->o_tilePtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileRec = takei((size_t)B * d.maxRec);
+    h->o_tileInjPtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileInj = takei((size_t)B * 4 * maxInj);
     h->n_int = oi;
+    h->fused = !h->sponge && pp->kernels == 0;
+    if (h->fused) {
+        CU(cudaFuncSetAttribute(k_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        CU(cudaFuncSetAttribute(k_fused_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
+        CU(cudaFuncSetAttribute(k_fused_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
+    }
     size_t of = 0;
     auto takef = [&](size_t n) { size_t o = of; of += n; return o; };
     h->o_amp = takef((size_t)B * d.nSteps); h->o_rxz = takef(B); h->o_w = takef((size_t)B * d.maxRec * 3);
@@ -318,6 +331,8 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     t.injPtr = h->t_int + h->o_injPtr; t.injRec = h->t_int + h->o_injRec;
     t.amp = h->t_flt + h->o_amp; t.rxz = h->t_flt + h->o_rxz; t.w = h->t_flt + h->o_w; t.injCoef = h->t_flt + h->o_injCoef;
     t.maxInj = maxInj; t.maxCon = maxCon;
+    t.tilePtr = h->t_int + h->o_tilePtr; t.tileRec = h->t_int + h->o_tileRec; t.nTiles = h->ntx * h->ntz; t.ntx = h->ntx;
+    t.tileInjPtr = h->t_int + h->o_tileInjPtr; t.tileInj = h->t_int + h->o_tileInj;
 
     // CPML profiles / sponge
     if (!h->sponge) {
@@ -442,6 +457,15 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
             if (sh.weights) { w[0] = sh.weights[3 * r]; w[1] = sh.weights[3 * r + 1]; w[2] = sh.weights[3 * r + 2]; }
             else { w[0] = h->p.fiber == SEPFWI_FIBER_EXX ? 1.f : 0.f; w[1] = h->p.fiber == SEPFWI_FIBER_EZZ ? 1.f : 0.f; w[2] = 0.f; }
         }
+        {   // receivers bucketed by fused-kernel tile (counting sort, stable in receiver index)
+            const int nT = h->ntx * h->ntz;
+            int *tp = h->h_int + h->o_tilePtr + (size_t)s * (nT + 1), *trc = h->h_int + h->o_tileRec + (size_t)s * d.maxRec;
+            std::fill(tp, tp + nT + 1, 0);
+            for (int r = 0; r < sh.nrec; r++) tp[(sh.zrec[r] / FTZ) * h->ntx + sh.xrec[r] / FTX + 1]++;
+            for (int t = 0; t < nT; t++) tp[t + 1] += tp[t];
+            std::vector<int> cur(tp, tp + nT);
+            for (int r = 0; r < sh.nrec; r++) trc[cur[(sh.zrec[r] / FTZ) * h->ntx + sh.xrec[r] / FTX]++] = r;
+        }
         // source amplitude per step
         float *amp = h->h_flt + h->o_amp + (size_t)s * d.nSteps;
         memcpy(amp, sh.stf, (size_t)d.nSteps * sizeof(float));
@@ -485,9 +509,32 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
             }
             ptr[nt] = (int)v.size();
             h->h_int[h->o_injN + s] = nt;
+            // bucket the targets by fused-kernel tile, halo of 2 included
+            const int nT = h->ntx * h->ntz;
+            int *tp = h->h_int + h->o_tileInjPtr + (size_t)s * (nT + 1), *tl = h->h_int + h->o_tileInj + (size_t)s * 4 * maxInj;
+            std::fill(tp, tp + nT + 1, 0);
+            auto for_tiles = [&](int m, auto &&fn) {
+                const int z = cell[m] / d.ldx, x = cell[m] % d.ldx;
+                const int tz0 = std::max(0, (z - 2) / FTZ), tz1 = std::min(h->ntz - 1, (z + 2) / FTZ);
+                const int tx0 = std::max(0, (x - 2) / FTX), tx1 = std::min(h->ntx - 1, (x + 2) / FTX);
+                for (int tz = tz0; tz <= tz1; tz++)
+                    for (int tx = tx0; tx <= tx1; tx++) {
+                        const int zz0 = tz * FTZ, xx0 = tx * FTX;
+                        if (z >= zz0 - 2 && z <= zz0 + FTZ + 1 && x >= xx0 - 2 && x <= xx0 + FTX + 1) fn(tz * h->ntx + tx);
+                    }
+            };
+            for (int m = 0; m < nt; m++) for_tiles(m, [&](int t) { tp[t + 1]++; });
+            for (int t = 0; t < nT; t++) tp[t + 1] += tp[t];
+            std::vector<int> cur(tp, tp + nT);
+            for (int m = 0; m < nt; m++) for_tiles(m, [&](int t) { tl[cur[t]++] = m; });
         }
     }
-    for (int s = nb; s < h->B; s++) { h->h_int[h->o_nrec + s] = 0; h->h_int[h->o_injN + s] = 0; }
+    for (int s = nb; s < h->B; s++) {
+        h->h_int[h->o_nrec + s] = 0; h->h_int[h->o_injN + s] = 0;
+        const int nT = h->ntx * h->ntz;
+        std::fill(h->h_int + h->o_tilePtr + (size_t)s * (nT + 1), h->h_int + h->o_tilePtr + (size_t)(s + 1) * (nT + 1), 0);
+        std::fill(h->h_int + h->o_tileInjPtr + (size_t)s * (nT + 1), h->h_int + h->o_tileInjPtr + (size_t)(s + 1) * (nT + 1), 0);
+    }
     CU(cudaMemcpyAsync(h->t_int, h->h_int, h->n_int * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->t_flt, h->h_flt, h->n_flt * sizeof(float), cudaMemcpyHostToDevice, st));
     return 0;
@@ -506,27 +553,37 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
     const Dims &d = h->d;
     KArgs a = kargs(h);
     const size_t slot_stride = d.sstride * sizeof(float);
-    const size_t live = (size_t)(NFIELD + NPSI) * d.fsz * sizeof(float);
+    const size_t live = (size_t)NSTATE_FWD * d.fsz * sizeof(float);
     for (int s = 0; s < nb; s++)
         CU(cudaMemsetAsync((char *)h->state + s * slot_stride, 0, live, st));
     CU(cudaMemsetAsync(h->trace, 0, (size_t)nb * d.nTrace * d.maxRec * d.nSteps * sizeof(float), st));
     dim3 blk(BX, BY), grd((d.nx + BX - 1) / BX, (d.nzA + BY - 1) / BY, nb);
     dim3 rgrd((mrec + 127) / 128, nb), ringgrd((d.ringLen + 255) / 256, nb);
     CU(cudaEventRecord(h->ev[0], st));
-    if (!h->sponge) {
+    if (h->fused) {
+        dim3 fgrd(h->ntx, h->ntz, nb);
+        for (int it = 0; it <= d.nSteps - 2; it++) {
+            const bool pr = it < h->prof_steps;
+            FusedFwdArgs fa;
+            fa.it = it; fa.mask = (it >= 1 && mrec > 0) ? mask : 0; fa.fiber = h->p.fiber; fa.save_ring = save_ring ? 1 : 0;
+            LAUNCH(h, SEPFWI_K_FUSED_FWD, pr, st, (k_fused_fwd<<<fgrd, F4_NT, F_SMEM, st>>>(a, fa)));
+        }
+        const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state
+        if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, false, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, d.nSteps - 1, mask, h->p.fiber, par)));
+    } else if (!h->sponge) {
         for (int it = 0; it <= d.nSteps - 2; it++) {
             const bool pr = it < h->prof_steps;
             if (save_ring) LAUNCH(h, SEPFWI_K_RING_SAVE, pr, st, (k_ring_save<<<ringgrd, 256, 0, st>>>(a, it)));
             LAUNCH(h, SEPFWI_K_STRESS_FWD, pr, st, (k_stress_fwd<false><<<grd, blk, 0, st>>>(a, it)));
             LAUNCH(h, SEPFWI_K_VELOCITY_FWD, pr, st, (k_velocity_fwd<false><<<grd, blk, 0, st>>>(a)));
-            if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, it + 1, mask, h->p.fiber)));
+            if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, it + 1, mask, h->p.fiber, 0)));
         }
     } else {
         for (int it = 0; it < d.nSteps; it++) {
             const bool pr = it < h->prof_steps;
             LAUNCH(h, SEPFWI_K_VELOCITY_FWD, pr, st, (k_velocity_fwd<true><<<grd, blk, 0, st>>>(a)));
             LAUNCH(h, SEPFWI_K_STRESS_FWD, pr, st, (k_stress_fwd<true><<<grd, blk, 0, st>>>(a, it)));
-            if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<true><<<rgrd, 128, 0, st>>>(a, it, mask, h->p.fiber)));
+            if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<true><<<rgrd, 128, 0, st>>>(a, it, mask, h->p.fiber, 0)));
         }
     }
     CU(cudaEventRecord(h->ev[1], st));
@@ -579,13 +636,27 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     const size_t slot_stride = d.sstride * sizeof(float);
     for (int s = 0; s < nb; s++)   // adjoint fields + adjoint memory variables restart from zero (libCUFD.cu:503-517)
         CU(cudaMemsetAsync((char *)h->state + s * slot_stride + (size_t)S_ADJ * d.fsz * sizeof(float), 0,
-                           (size_t)(NFIELD + NPSI) * d.fsz * sizeof(float), st));
+                           (size_t)(NSTATE - NSTATE_FWD) * d.fsz * sizeof(float), st));
     CU(cudaMemsetAsync(h->gstf, 0, (size_t)nb * d.nSteps * sizeof(float), st));
     dim3 blk(BX, BY), grd((d.nx + BX - 1) / BX, (d.nzA + BY - 1) / BY, nb);
     const int rx = d.x1 + 2 - (d.nPml - 2) + 1, rz = d.z1 + 2 - (d.nPml - 2) + 1;
     dim3 rgrd((rx + BX - 1) / BX, (rz + BY - 1) / BY, nb);
     dim3 igrd((minj + 127) / 128, nb);
     CU(cudaEventRecord(h->ev[2], st));
+    if (h->fused) {
+        dim3 agrd(h->ntx, h->ntz, nb);
+        const int xbase = (d.nPml - 2) & ~3;
+        dim3 cgrd((d.x1 + 2 - xbase) / FTX + 1, (d.z1 + 2 - (d.nPml - 2)) / FTZ + 1, nb);
+        int q = (d.nSteps - 1) & 1, pa = 0;     // forward state nSteps-1 sits in buffer q; adjoint starts in buffer 0
+        for (int it = d.nSteps - 2; it >= 0; it--) {
+            const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
+            FusedBwdArgs fa;
+            fa.it = it; fa.q = q; fa.pa = pa;
+            LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F_NT, R_SMEM, st>>>(a, fa)));
+            LAUNCH(h, SEPFWI_K_FUSED_ADJ, pr, st, (k_fused_adj<<<agrd, F_NT, A_SMEM, st>>>(a, fa)));
+            q ^= 1; pa ^= 1;
+        }
+    } else
     for (int it = d.nSteps - 2; it >= 0; it--) {
         const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
         LAUNCH(h, SEPFWI_K_VELOCITY_BWD, pr, st, (k_velocity_bwd<<<rgrd, blk, 0, st>>>(a, it)));

@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))     # .../sep-2023_b200
-LIB_PATH = os.path.join(_PKG, "libsepfwi.so")
+LIB_PATH = os.environ.get("SEPFWI_LIB") or os.path.join(_PKG, "libsepfwi.so")   # SEPFWI_LIB: alternate build (tuning experiments)
 
 FIBER_EXX, FIBER_EZZ = 0, 1
 FLAVOUR_CPML, FLAVOUR_SPONGE = 0, 1
@@ -38,7 +38,7 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
            "sepfwi_kernel_name"]
-NKERNEL = 11
+NKERNEL = 12
 
 _lib = None
 

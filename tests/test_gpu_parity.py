@@ -45,6 +45,29 @@ def test_forward_traces_match_oracle(mk, batch):
         assert P.launches > 0
 
 
+@pytest.mark.parametrize("mk,batch", [(problems.tiny, 2), (problems.small, 3), (lambda: problems.tiny(fiber=1), 1)])
+def test_fused_kernels_match_baseline_kernels(mk, batch):
+    """Default (fused, ping-pong, halo-recompute) path vs the unfused baseline kernels: same per-cell
+    arithmetic, so forward traces and gradients agree to rounding of differently contracted FMAs."""
+    O, Propagator, ShotSpec = _mods()
+    prob = mk()
+    res = {}
+    for kern in (0, 1):
+        with make_prop(Propagator, prob, max_batch=batch, with_adjoint=True, kernels=kern) as P:
+            P.set_model(*prob.true)
+            shots = cuda_shots(prob, ShotSpec)
+            fwd = P.forward(shots)
+            P.set_model(*prob.start)
+            g = P.gradient(shots, [f["ett"] for f in fwd])
+            res[kern] = (fwd, g)
+    for sid in range(prob.nshots):
+        for c in ("pr", "vx", "vz", "ett"):
+            assert rel_l2(res[0][0][sid][c], res[1][0][sid][c]) < 1e-5, (sid, c)
+    assert abs(res[0][1]["misfit"] - res[1][1]["misfit"]) <= 1e-5 * abs(res[1][1]["misfit"])
+    for k in ("glam", "gmu", "grho"):
+        assert rel_l2(res[0][1][k], res[1][1][k]) < 5e-5, k
+
+
 def test_cpml_profiles_match_oracle():
     O, Propagator, _ = _mods()
     prob = problems.small()
