@@ -652,8 +652,8 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
             const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
             FusedBwdArgs fa;
             fa.it = it; fa.q = q; fa.pa = pa;
-            LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F_NT, R_SMEM, st>>>(a, fa)));
-            LAUNCH(h, SEPFWI_K_FUSED_ADJ, pr, st, (k_fused_adj<<<agrd, F_NT, A_SMEM, st>>>(a, fa)));
+            LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F4_NT, R_SMEM, st>>>(a, fa)));
+            LAUNCH(h, SEPFWI_K_FUSED_ADJ, pr, st, (k_fused_adj<<<agrd, F4_NT, A_SMEM, st>>>(a, fa)));
             q ^= 1; pa ^= 1;
         }
     } else
