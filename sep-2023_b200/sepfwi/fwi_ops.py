@@ -59,8 +59,9 @@ def _prop(para, device, with_adjoint, nrec, nshots):
     fiber = _lib.FIBER_EZZ if para.get("das_component", "exx") == "ezz" else _lib.FIBER_EXX
     B = int(para.get("max_batch", 0)) or auto_batch(para["nz"], para["nx"], para["nPad"], para["nSteps"], nrec,
                                                     para["nPoints_pml"], with_adjoint, nshots, device)
+    race = bool(para.get("ref_race_compat", False))
     key = (device, para["nz"], para["nx"], para["nPoints_pml"], para["nPad"], para["nSteps"], float(para["dz"]),
-           float(para["dx"]), float(para["dt"]), float(para["f0"]), fiber, bool(with_adjoint))
+           float(para["dx"]), float(para["dt"]), float(para["f0"]), fiber, bool(with_adjoint), race)
     with _LOCK:
         p = _PROPS.get(key)
         if p is not None and (p.params.max_nrec < nrec or p.params.max_batch < min(B, nshots)):
@@ -69,7 +70,7 @@ def _prop(para, device, with_adjoint, nrec, nshots):
         if p is None:
             p = Propagator(para["nz"], para["nx"], para["nPoints_pml"], para["nPad"], para["nSteps"], para["dz"],
                            para["dx"], para["dt"], para["f0"], fiber=fiber, max_batch=B, max_nrec=nrec,
-                           with_adjoint=with_adjoint, device=device)
+                           with_adjoint=with_adjoint, device=device, ref_race_compat=race)
             _PROPS[key] = p
     return p
 

@@ -20,9 +20,10 @@ def padded_shape(nz, nx, nPml):
 
 def paraGen(nz, nx, dz, dx, nSteps, dt, f0, nPml, nPad, para_fname, survey_fname, data_dir_name,
             if_win=False, filter_para=None, if_src_update=False, scratch_dir_name='', if_cross_misfit=False,
-            das_component=None, max_batch=None):
-    """Write para_file.json.  `das_component` ('exx' | 'ezz') and `max_batch` are extensions of this
-    implementation (the reference selects the fiber direction by editing libCUFD.cu:327-332)."""
+            das_component=None, max_batch=None, ref_race_compat=None):
+    """Write para_file.json.  `das_component` ('exx' | 'ezz'), `max_batch` and `ref_race_compat` are extensions of
+    this implementation (the reference selects the fiber direction by editing libCUFD.cu:327-332; ref_race_compat
+    reproduces the lost update of its racy residual injection, see include/sepfwi.h)."""
     para = {'nz': nz, 'nx': nx, 'dz': dz, 'dx': dx, 'nSteps': nSteps, 'dt': dt, 'f0': f0,
             'nPoints_pml': nPml, 'nPad': nPad}
     if if_win:
@@ -43,6 +44,8 @@ def paraGen(nz, nx, dz, dx, nSteps, dt, f0, nPml, nPad, para_fname, survey_fname
         para['das_component'] = das_component
     if max_batch is not None:
         para['max_batch'] = int(max_batch)
+    if ref_race_compat:
+        para['ref_race_compat'] = True
     with open(para_fname, 'w') as fp:
         json.dump(para, fp)
     return para

@@ -1,0 +1,159 @@
+"""GPU tests of the reference-facing Python API (run with -m gpu): the GPU-backed elasticSolver against
+the Numba golden vectors, the fwi_ops / FWI autograd front-end with its file side channels, and the
+reference's own published L-BFGS log values."""
+import os
+
+import numpy as np
+import pytest
+
+import problems
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["numba_homog", "numba_hetero"])
+def test_elastic_solver_matches_numba_reference(golden_dir, name):
+    """north_star: DAS seismograms within 1e-4 relative L2 of the Numba CPU modelling, computing in fp32."""
+    from sepfwi.elasticSolver import elasticSolver
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    kw = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
+    args = {k: (v.item() if v.ndim == 0 else v) for k, v in kw.items()}
+    solver = elasticSolver(**args)
+    sol = solver.forward()
+    assert len(sol) == kw["src_coord"].shape[0]
+    for isrc, s in enumerate(sol):
+        for k in ("vx", "vz", "pr", "ett", "exx", "ezz", "exz"):
+            ref = g["out%d_%s" % (isrc, k)]
+            assert s[k].shape == ref.shape and s[k].dtype == np.float64
+            assert rel_l2(s[k], ref) < 1e-4, (name, isrc, k, rel_l2(s[k], ref))
+    one = solver.forward_it(0, False)
+    assert np.array_equal(one["ett"], sol[0]["ett"])
+    with pytest.raises(ValueError):
+        solver.set_model(kw["vp"][:-1], kw["vs"][:-1], kw["rho"][:-1])
+
+
+def _write_problem(prob, tmp, **para_kw):
+    from sepfwi import fwi_utils as ft
+    para, survey, data = os.path.join(tmp, "para.json"), os.path.join(tmp, "survey.json"), os.path.join(tmp, "Data")
+    ft.paraGen(prob.nz, prob.nx, prob.dz, prob.dx, prob.nSteps, prob.dt, prob.f0, prob.nPml, prob.nPad, para, survey, data, **para_kw)
+    ft.surveyGen(prob.z_src, prob.x_src, prob.z_rec, prob.x_rec, survey)
+    return para, data
+
+
+def test_fwi_ops_matches_oracle_through_files(tmp_path):
+    """obscalc -> Shot_*.bin -> backward / forward, CPU tensors in, CPU tensors out (the reference's calling convention)."""
+    import torch
+    from oracle import oracle as O
+    from sepfwi import fwi_ops
+    from util import oracle_par
+    prob = problems.tiny()
+    para, data = _write_problem(prob, str(tmp_path))
+    ids = torch.arange(prob.nshots, dtype=torch.int32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    stf = T(prob.stf)
+    fwi_ops.obscalc(*map(T, prob.true), stf, 1, ids, para)
+    par = oracle_par(O, prob)
+    obs = {}
+    for sid, (zs, xs, zr, xr) in prob.survey().items():
+        ref = O.forward(par, *prob.true, prob.stf[sid], zs, xs, zr, xr)
+        for c in ("pr", "vx", "vz", "ett"):
+            got = np.fromfile(os.path.join(data, "Shot_%s%d.bin" % (c, sid)), np.float32).reshape(len(zr), prob.nSteps)
+            assert rel_l2(got, ref[c]) < 2e-5
+        obs[sid] = np.fromfile(os.path.join(data, "Shot_ett%d.bin" % sid), np.float32).reshape(len(zr), prob.nSteps)
+    J, gl, gm, gd, gs = O.fwi_backward(par, *prob.start, prob.stf, 1, np.arange(prob.nshots), prob.survey(), obs)
+    out = fwi_ops.backward(*map(T, prob.start), stf, 1, ids, para)
+    assert not out[1].is_cuda and out[0].shape == (1,)
+    assert abs(out[0].item() - J) <= 2e-5 * J
+    for got, ref in zip(out[1:], (gl, gm, gd, gs)):
+        assert rel_l2(got.numpy(), ref) < 2e-4
+    assert abs(fwi_ops.forward(*map(T, prob.start), stf, 0, ids, para)[0].item() - J) <= 2e-5 * J
+    # CUDA tensors in -> CUDA tensors out, same numbers
+    outc = fwi_ops.backward(*[T(a).cuda() for a in prob.start], stf, 1, ids, para)
+    assert outc[1].is_cuda and torch.equal(outc[1].cpu(), out[1])
+    # a subset of the shots, in a different order, fills exactly those stf-gradient rows
+    out1 = fwi_ops.backward(*map(T, prob.start), stf, 1, torch.tensor([1], dtype=torch.int32), para)
+    assert torch.all(out1[4][0] == 0) and torch.equal(out1[4][1], out[4][1])
+    with pytest.raises(RuntimeError):
+        fwi_ops.backward(*map(T, prob.start), stf, 3, ids, para)       # more GPUs than shots
+    fwi_ops.clear_cache()
+
+
+def test_multi_gpu_in_process_equals_single_gpu(tmp_path):
+    """ngpu = 2 (threads over GPUs 0,1, like the reference's OpenMP loop) gives the single-GPU sums."""
+    import torch
+    from sepfwi import fwi_ops
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    prob = problems.small()
+    para, data = _write_problem(prob, str(tmp_path))
+    ids = torch.arange(prob.nshots, dtype=torch.int32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    stf = T(prob.stf)
+    fwi_ops.obscalc(*map(T, prob.true), stf, 2, ids, para)
+    a = fwi_ops.backward(*map(T, prob.start), stf, 1, ids, para)
+    b = fwi_ops.backward(*map(T, prob.start), stf, 2, ids, para)
+    assert abs(a[0].item() - b[0].item()) <= 1e-6 * abs(a[0].item())
+    for x, y in zip(a[1:], b[1:]):
+        assert rel_l2(y.numpy(), x.numpy()) < 1e-6
+    fwi_ops.clear_cache()
+
+
+def test_reference_notebook_lbfgs_iterate0(tmp_path):
+    """The reference's own published numbers (notebooks/001-FWI-Anomaly-Vp-Vs-Den.ipynb cell 7 output):
+        At iterate 0  f = 1.51116D+04  |proj g| = 2.14289D+00
+    for the fully in-notebook-specified anomaly problem (cell 3; Main-001-...py:28-135): 101 x 201, 19 shots,
+    181 ADJACENT receivers, nt = 1501, FWI module with the top-4-rows mask, homogeneous start.
+    f(x0) only involves the forward path.  |proj g| is max |dJ/d(Vp,Vs,Den)| and carries the reference's
+    residual-injection race (adjacent receivers straddle five 32-thread block seams), so it is compared with
+    ref_race_compat on; the race-free gradient is reported alongside."""
+    import torch
+    from sepfwi import FWI_ops as F, fwi_ops, fwi_utils as ft
+    nz, nx, nPml, dz, dx, dt, nt, f0 = 101, 201, 32, 20.0, 20.0, 0.002, 1501, 10.0
+    nz_pad, nx_pad, nPad = ft.padded_shape(nz, nx, nPml)
+    vp = np.ones((nx, nz)) * 4000.0
+    vs = np.ones((nx, nz)) * 4000.0 / 1.732
+    rho = np.ones((nx, nz)) * 2500.0
+    vp[42:58, 42:58] += 80.0
+    vs[92:108, 42:58] -= 80.0 / 1.732
+    rho[142:158, 42:58] += 40
+    true = [a.T.astype("float32") for a in (vp, vs, rho)]              # saved transposed, loaded as float32
+    init = [np.full((nz, nx), v, "float32") for v in (4000.0, 4000.0 / 1.732, 2500.0)]
+    x_src = np.arange(10, nx - 10, 10).astype(int)
+    z_src = np.ones(len(x_src), int)
+    x_rec = np.arange(10, nx - 10).astype(int)
+    z_rec = 95 * np.ones(len(x_rec), int)
+    Mask = np.zeros((nz_pad, nx_pad))
+    Mask[nPml:nPml + nz, nPml:nPml + nx] = 1.0
+    Mask[nPml:nPml + 4, :] = 0.0
+    stf = torch.tensor(ft.sourceGene(f0, nt, dt), dtype=torch.float32).repeat(len(x_src), 1)
+    ids = torch.tensor(np.arange(len(x_src)), dtype=torch.int32)
+    res = {}
+    for compat in (True, False):
+        work = str(tmp_path / ("c%d" % compat))
+        os.makedirs(work)
+        para, survey, data = work + "/para_file.json", work + "/survey_file.json", work + "/Data"
+        ft.paraGen(nz_pad, nx_pad, dz, dx, nt, dt, f0, nPml, nPad, para, survey, data, ref_race_compat=compat)
+        ft.surveyGen(z_src, x_src, z_rec, x_rec, survey)
+        pads = [torch.tensor(ft.padding_numpy_array(a, nPml, nPad), dtype=torch.float32) for a in true]
+        F.FWI_obscalc(*pads, stf, para)(ids, ngpu=1)
+        opt = dict(nz=nz, nx=nx, nz_orig=nz, nx_orig=nx, nPml=nPml, nPad=nPad, para_fname=para)
+        th = [torch.tensor(a, dtype=torch.float32, requires_grad=True) for a in init]
+        fwi = F.FWI(*th, stf, opt, Mask=torch.tensor(Mask, dtype=torch.float32))
+        loss = fwi(ids, ngpu=1)
+        loss.backward()
+        g = np.concatenate([p.grad.numpy().astype(np.float64).ravel() for p in (fwi.Vp, fwi.Vs, fwi.Den)])
+        assert g.size == 60903                                         # "N = 60903" in the log
+        res[compat] = (loss.item(), np.abs(g).max())
+    msg = ("f(x0) = %.6e (reference log 1.51116e+04); |proj g| = %.6f with the seam update lost as on B200, %.6f race-free "
+           "(reference log 2.14289, 4 GPUs of another generation)" % (res[True][0], res[True][1], res[False][1]))
+    print(msg)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        open(os.path.join(out, "notebook_golden.txt"), "w").write(msg + "\n")
+    assert abs(res[True][0] - 1.51116e4) <= 1e-5 * 1.51116e4 * 2      # printed with 6 significant digits
+    assert res[False][0] == res[True][0]                               # the misfit does not involve the adjoint
+    # which update the reference's race loses depends on its block scheduling (hardware / driver): the logged value
+    # cannot be pinned to 6 digits, only bracketed by the two deterministic gradients
+    assert min(abs(res[True][1] - 2.14289), abs(res[False][1] - 2.14289)) <= 0.02 * 2.14289
+    fwi_ops.clear_cache()

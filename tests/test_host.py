@@ -1,0 +1,169 @@
+"""CPU tests of the host layer (no compute calls: there is no GPU in the build container).
+
+ * libsepfwi.so loads and exports every symbol include/sepfwi.h declares;
+ * without a CUDA device every compute entry fails loudly (no CPU fallback);
+ * para/survey JSON writers, padding rule, Ricker, survey parser (Src_Rec index shift);
+ * shot sharding + the packed all-reduce on two gloo ranks;
+ * the product package never imports the oracle.
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from sepfwi import _lib
+    hdr = open(os.path.join(ROOT, "include", "sepfwi.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sepfwi_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (sepfwi_[a-z0-9_]+)", out))
+    assert declared <= exported
+    assert L.sepfwi_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of sepfwi_params / sepfwi_shot have the C sizes (checked against a compiled probe)."""
+    import ctypes as C
+    from sepfwi import _lib
+    src = '#include <stdio.h>\n#include "sepfwi.h"\nint main(){printf("%zu %zu\\n", sizeof(sepfwi_params), sizeof(sepfwi_shot));return 0;}\n'
+    exe = os.path.join(ROOT, "tests", "_probe_sizes")
+    p = subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True,
+                       capture_output=True)
+    assert p.returncode == 0, p.stderr
+    a, b = map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split())
+    os.unlink(exe)
+    assert C.sizeof(_lib.Params) == a and C.sizeof(_lib.Shot) == b
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from sepfwi._lib import SepfwiError
+    from sepfwi.engine import Propagator
+    with pytest.raises(SepfwiError) as e:
+        Propagator(64, 64, 8, 0, 10, 10.0, 10.0, 1e-3, 10.0)
+    assert "no CPU fallback" in str(e.value) or e.value.code == -2
+    # the cufd drop-in reports through its return code as well
+    import ctypes as C
+    from sepfwi import _lib
+    z = np.zeros((4, 4), np.float32)
+    ids = np.zeros(1, np.int32)
+    rc = _lib.lib().sepfwi_cufd(None, None, None, None, None, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 2, 0, 1,
+                                ids.ctypes.data, b"/nonexistent/para.json")
+    assert rc == -4 and b"parameter file" in _lib.lib().sepfwi_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sep-2023_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "README.md", os.path.join(dirpath, f)
+
+
+def test_para_and_survey_files(tmp_path):
+    from sepfwi import fwi_utils as ft
+    para, survey, data = str(tmp_path / "para.json"), str(tmp_path / "survey.json"), str(tmp_path / "data")
+    nz, nx, nPad = ft.padded_shape(101, 201, 32)
+    assert (nz, nx, nPad) == (192, 265, 27)
+    assert ft.padded_shape(64, 96, 16)[2] == 32                # already aligned -> a full 32
+    ft.paraGen(nz, nx, 20.0, 20.0, 1501, 0.002, 10.0, 32, nPad, para, survey, data)
+    ft.surveyGen(np.full(3, 1), np.array([10, 20, 30]), np.full(5, 95), np.arange(10, 15), survey, Src_rxz=[1.0, 0.5, 2.0])
+    for fn in (para, survey):
+        txt = open(fn).read()
+        assert "\n" not in txt                                  # the C++ readers only take the first line
+        json.loads(txt)
+    p = ft.read_json_first_line(para)
+    assert p["nPoints_pml"] == 32 and p["nSteps"] == 1501 and p["survey_fname"] == survey and os.path.isdir(data)
+    sv = ft.load_survey(survey, [2, 0], 32)
+    assert sv[0]["xs"] == 30 + 32 and sv[0]["zs"] == 1 + 32 and sv[0]["src_rxz"] == 2.0
+    assert np.array_equal(sv[1]["xrec"], np.arange(10, 15) + 32) and np.all(sv[1]["zrec"] == 95 + 32)
+
+
+def test_ricker_and_padding():
+    import torch
+    from sepfwi import fwi_utils as ft
+    s = ft.sourceGene(10.0, 1501, 0.002)
+    k = int(round(1.2 / 10.0 / 0.002))
+    assert s.argmax() == k and s[k] == pytest.approx(1.0e7)
+    a = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    p = ft.padding(a, a, a, 3, 4, 3, 4, 2, 1)[0]
+    assert tuple(p.shape) == (3 + 4 + 1, 4 + 4)
+    assert torch.equal(p[2:5, 2:6], a) and torch.all(p[0, 2:6] == a[0]) and torch.all(p[-1, 2:6] == a[-1])
+    assert np.array_equal(ft.padding_numpy_array(a.numpy(), 2, 1), p.numpy())
+
+
+def test_shard_bounds_and_errors():
+    from sepfwi import dist
+    assert dist.shard_bounds(19, 4) == [0, 4, 9, 14, 19]       # Torch_Fwi.cpp:59-60
+    assert dist.shard(list(range(19)), 4, 1) == [4, 5, 6, 7, 8]
+    with pytest.raises(RuntimeError):
+        dist.shard([0, 1], 3, 0)                               # more GPUs than shots (Torch_Fwi.cpp:49-52)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "sep-2023_b200"))
+import torch, torch.distributed as td
+from sepfwi import dist
+rank = int(sys.argv[1])
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=2)
+ids = dist.shard(list(range(5)), 2, rank)                       # 2 + 3 shots
+assert ids == ([0, 1] if rank == 0 else [2, 3, 4]), ids
+g = [torch.full((3, 4), float(rank + 1) * k) for k in (1, 2, 3)]
+gstf = torch.zeros(5, 7)
+for i in ids:
+    gstf[i] = i + 1
+J, gl, gm, gd, gs = dist.allreduce_gradients(10.0 * (rank + 1), g[0], g[1], g[2], gstf)
+assert abs(J - 30.0) < 1e-6 and torch.all(gl == 3) and torch.all(gm == 6) and torch.all(gd == 9)
+assert torch.equal(gs[:, 0], torch.arange(1, 6, dtype=torch.float32))   # every shot's stf row survives the reduction
+td.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_packed_allreduce_on_two_gloo_ranks(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % dict(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    for r, p in enumerate(procs):
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok %d" % r in out, err[-2000:]
+
+
+def test_fwi_module_parameterisations_map_to_lame():
+    """The parameterisation maps (FWI_ops.py:124-125, 263-266, 324-328, 390-392) without running the op."""
+    import torch
+    from sepfwi import FWI_ops as F
+    vp, vs, den = torch.tensor([3000.0]), torch.tensor([1700.0]), torch.tensor([2200.0])
+    lam, mu, d = F.FWI.to_lame(vp, vs, den)
+    assert mu.item() == pytest.approx(1700.0 ** 2 * 2200.0 / 1e6) and lam.item() == pytest.approx((3000.0 ** 2 - 2 * 1700.0 ** 2) * 2200.0 / 1e6)
+    ip, is_ = vp * den / 1e3, vs * den / 1e3                    # impedances scaled so that IP^2/Den is in MPa
+    l2, m2, _ = F.FWI_IP_IS_Den.to_lame(ip, is_, den)
+    assert l2.item() == pytest.approx(lam.item(), rel=1e-6) and m2.item() == pytest.approx(mu.item(), rel=1e-6)
+    l3, m3, d3 = F.FWI_Vp_Vs_IP.to_lame(vp, vs, vp * den)
+    assert d3.item() == pytest.approx(2200.0) and m3.item() == pytest.approx(1700.0 ** 2 * 2200.0)
+    l4, m4, d4 = F.FWI_Vp_Vs_IS.to_lame(vp, vs, vs * den)
+    assert d4.item() == pytest.approx(2200.0) and l4.item() == pytest.approx(l3.item(), rel=1e-6) and m4.item() == pytest.approx(m3.item(), rel=1e-6)
+    assert F.FWI_Lame_Den.to_lame(lam, mu, den) == (lam, mu, den)
