@@ -69,7 +69,7 @@ typedef struct sepfwi_params {
     int   max_batch;       /* shots propagated concurrently on the device (>= 1)                                       */
     int   max_nrec;        /* upper bound of receivers per shot                                                        */
     int   with_adjoint;    /* 1: allocate boundary store + adjoint state (needed by sepfwi_gradient with_adj)          */
-    int   kernels;         /* 0: default (fastest validated path), 1: force the unfused baseline kernels               */
+    int   kernels;         /* 0: default (register-streaming kernels), 1: unfused baseline kernels, 2: shared-memory tile kernels */
     int   ref_race_compat; /* 0 (default): race-free adjoint source.  1: reproduce the reference's lost update in
                               res_injection_exx/_ezz (utilities.cu:613-614,639-640, launched 32 receivers per block):
                               when receiver 32k subtracts at the cell receiver 32k-1 adds to, the subtraction is dropped.
@@ -146,7 +146,8 @@ int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
  * accumulated milliseconds and launch counts per kernel kind since the last sepfwi_set_profile. */
 enum { SEPFWI_K_RING_SAVE = 0, SEPFWI_K_STRESS_FWD, SEPFWI_K_VELOCITY_FWD, SEPFWI_K_RECORD, SEPFWI_K_VELOCITY_BWD,
        SEPFWI_K_STRESS_BWD, SEPFWI_K_VELOCITY_ADJ, SEPFWI_K_INJECT, SEPFWI_K_STRESS_ADJ, SEPFWI_K_FUSED_FWD,
-       SEPFWI_K_FUSED_RECON, SEPFWI_K_FUSED_ADJ, SEPFWI_NKERNEL };
+       SEPFWI_K_FUSED_RECON, SEPFWI_K_FUSED_ADJ, SEPFWI_K_STREAM_FWD, SEPFWI_K_STREAM_RECON, SEPFWI_K_STREAM_ADJ,
+       SEPFWI_NKERNEL };
 int sepfwi_set_profile(sepfwi_handle *h, int nsteps);
 int sepfwi_get_profile(sepfwi_handle *h, double *ms /*[SEPFWI_NKERNEL]*/, long long *count /*[SEPFWI_NKERNEL]*/);
 const char *sepfwi_kernel_name(int kind);

@@ -87,6 +87,8 @@ struct KArgs {
     const float *model;  // [NMODEL][fsz]
     const float *cz;     // [NCOEF][nzA]
     const float *cx;     // [NCOEF][nx]
+    const float *cxs;    // [NCOEF][ldx] x profiles for the stress-side CPML, neutral (1/K = 1, a = b = 0) outside x < nPml || x > nx-nPml-1
+    const float *cxv;    // [NCOEF][ldx] same for the velocity side: neutral outside x < nPml || x > nx-nPml (el_velocity.cu:56,71)
     const float *damp;   // sponge flavour: [fsz] multiplicative profile (NULL otherwise)
     float *ring;         // [slot][NFIELD][nSteps][ringLen]
     float *trace;        // [slot][nTrace][maxRec*nSteps]

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -19,6 +20,7 @@
 #include "kernels_base.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_fused_bwd.cuh"
+#include "kernels_stream.cuh"
 
 using namespace sepfwi;
 
@@ -48,7 +50,7 @@ struct sepfwi_handle {
     int B;                 // slots
     bool sponge;
     // device arenas
-    float *state = nullptr, *model = nullptr, *cz = nullptr, *cx = nullptr, *damp = nullptr;
+    float *state = nullptr, *model = nullptr, *cz = nullptr, *cx = nullptr, *cxs = nullptr, *cxv = nullptr, *damp = nullptr;
     float *ring = nullptr, *trace = nullptr, *grad = nullptr, *gstf = nullptr;
     float *dense[3] = {nullptr, nullptr, nullptr};   // [nz][nx] staging for model in / gradient out
     int *maxcp = nullptr;
@@ -61,7 +63,11 @@ struct sepfwi_handle {
     // offsets (in elements) of the packed tables
     size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_tilePtr, o_tileRec, o_tileInjPtr, o_tileInj;
     int ntx = 0, ntz = 0;
-    bool fused = false;
+    bool fused = false;    // tile kernels (kernels = 2); their backward half also serves kernels = 0 until the streaming one lands
+    bool stream = false;   // register-streaming kernels (kernels = 0)
+    int nSM = 148;
+    int4 *work = nullptr;  // work list of the streaming kernels (device)
+    size_t work_cap = 0;
     size_t o_amp, o_rxz, o_w, o_injCoef;
     bool use_w = false;
     // host copies
@@ -82,7 +88,7 @@ struct sepfwi_handle {
 };
 
 static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
-                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_recon", "fused_adj"};
+                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_recon", "fused_adj", "stream_fwd", "stream_recon", "stream_adj"};
 
 // launch `stmt` and, in profile mode, bracket it with an event pair
 #define LAUNCH(h, KND, prof_on, st, stmt)                                     \
@@ -222,7 +228,7 @@ extern "C" int sepfwi_ring_len(const sepfwi_params *p)
 static KArgs kargs(const sepfwi_handle *h)
 {
     KArgs a;
-    a.d = h->d; a.state = h->state; a.model = h->model; a.cz = h->cz; a.cx = h->cx; a.damp = h->damp;
+    a.d = h->d; a.state = h->state; a.model = h->model; a.cz = h->cz; a.cx = h->cx; a.cxs = h->cxs; a.cxv = h->cxv; a.damp = h->damp;
     a.ring = h->ring; a.trace = h->trace; a.grad = h->grad; a.gstf = h->gstf; a.t = h->tab;
     if (!h->use_w) a.t.w = nullptr;
     return a;
@@ -232,10 +238,11 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    float *fp[] = {h->state, h->model, h->cz, h->cx, h->damp, h->ring, h->trace, h->grad, h->gstf,
+    float *fp[] = {h->state, h->model, h->cz, h->cx, h->cxs, h->cxv, h->damp, h->ring, h->trace, h->grad, h->gstf,
                    h->dense[0], h->dense[1], h->dense[2], h->t_flt};
     for (float *q : fp) if (q) cudaFree(q);
     if (h->maxcp) cudaFree(h->maxcp);
+    if (h->work) cudaFree(h->work);
     if (h->partial) cudaFree(h->partial);
     if (h->misfit) cudaFree(h->misfit);
     if (h->t_int) cudaFree(h->t_int);
@@ -282,6 +289,8 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     ALLOC(h->model, (size_t)NMODEL * d.fsz * sizeof(float));
     ALLOC(h->cz, (size_t)NCOEF * d.nzA * sizeof(float));
     ALLOC(h->cx, (size_t)NCOEF * d.nx * sizeof(float));
+    ALLOC(h->cxs, (size_t)NCOEF * d.ldx * sizeof(float));
+    ALLOC(h->cxv, (size_t)NCOEF * d.ldx * sizeof(float));
     ALLOC(h->trace, (size_t)B * d.nTrace * d.maxRec * d.nSteps * sizeof(float));
     ALLOC(h->gstf, (size_t)B * d.nSteps * sizeof(float));
     for (int k = 0; k < 3; k++) ALLOC(h->dense[k], (size_t)d.nz * d.nx * sizeof(float));
@@ -307,7 +316,13 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     h->o_tilePtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileRec = takei((size_t)B * d.maxRec);
     h->o_tileInjPtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileInj = takei((size_t)B * 4 * maxInj);
     h->n_int = oi;
-    h->fused = !h->sponge && pp->kernels == 0;
+    h->stream = !h->sponge && pp->kernels == 0;
+    h->fused = !h->sponge && (pp->kernels == 0 || pp->kernels == 2);
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        h->nSM = prop.multiProcessorCount;
+    }
     if (h->fused) {
         CU(cudaFuncSetAttribute(k_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         CU(cudaFuncSetAttribute(k_fused_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
@@ -344,6 +359,19 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         h->hcx.insert(h->hcx.end(), kx.begin(), kx.end());
         CU(cudaMemcpy(h->cz, h->hcz.data(), (size_t)NCOEF * d.nzA * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->cx, h->hcx.data(), (size_t)NCOEF * d.nx * sizeof(float), cudaMemcpyHostToDevice));
+        // quad-aligned copies for the streaming kernels, neutral wherever the reference kernel skips the CPML branch
+        std::vector<float> ts((size_t)NCOEF * d.ldx), tv((size_t)NCOEF * d.ldx);
+        for (int x = 0; x < d.ldx; x++) {
+            const bool ins = x < d.nx && ((x < d.nPml) || (x > d.nx - d.nPml - 1));     // el_stress.cu:63
+            const bool inv = x < d.nx && ((x < d.nPml) || (x > d.nx - d.nPml));         // el_velocity.cu:56,71
+            for (int k = 0; k < NCOEF; k++) {
+                const float neutral = (k == C_RK || k == C_RKH) ? 1.0f : 0.0f;
+                ts[(size_t)k * d.ldx + x] = ins ? h->hcx[(size_t)k * d.nx + x] : neutral;
+                tv[(size_t)k * d.ldx + x] = inv ? h->hcx[(size_t)k * d.nx + x] : neutral;
+            }
+        }
+        CU(cudaMemcpy(h->cxs, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->cxv, tv.data(), tv.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else {
         // multiplicative sponge sin^2(pi/2 i/ndamp) from all four sides, elasticSolver.py:74-79
         std::vector<float> dm(d.fsz, 1.0f);
@@ -547,6 +575,63 @@ static int max_nrec(int nb, const sepfwi_shot *shots)
     return m;
 }
 
+// Work list of the streaming kernels: 120-column strips x row chunks, one warp each.
+//   * rows [0, nPml+2) and [nzA-nPml-2, nzA) and the strips that touch the x CPML / rim are "edge" items (slower per row:
+//     CPML memory variables, no look-ahead): they get shorter chunks and are listed first so they never form the tail;
+//   * interior chunks are Lz rows with (Lz + 4) a multiple of the 6-row unroll, Lz chosen so that the item count fills whole
+//     waves of nSM x 8 resident warps (2 CTAs x 4 warps at 255 registers).  SEPFWI_LZ / SEPFWI_LZE override the two heights.
+static int stream_plan(sepfwi_handle *h, int nb, StreamArgs &sa)
+{
+    const Dims &d = h->d;
+    memset(&sa, 0, sizeof(sa));
+    const int nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
+    const int zi0 = d.nPml + 2, zi1 = d.nzA - d.nPml - 2;      // interior rows [zi0, zi1)
+    const double conc = (double)h->nSM * 2 * SW_WPB;
+    const double edge_cost = 1.8;
+    auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml && x0 + SW_OWN + 3 <= d.nx - d.nPml - 1; };
+    int nInnerStrips = 0;
+    for (int sx = 0; sx < nStrips; sx++) nInnerStrips += strip_inner(sx) ? 1 : 0;
+    int best = 8;
+    double bestc = 1e300;
+    for (int Lz = 8; Lz <= 128; Lz += 6) {
+        const int nch = (zi1 - zi0 + Lz - 1) / Lz;
+        const int Le = std::max(4, (int)((Lz + 4) / edge_cost) - 4);
+        const int nche = (zi1 - zi0 + Le - 1) / Le, ntb = 2 * ((zi0 + Le - 1) / Le);
+        const double items = (double)nInnerStrips * nch + (double)(nStrips - nInnerStrips) * nche + (double)nStrips * ntb;
+        const double c = ceil(items * nb / conc) * (Lz + 4 + 3);
+        if (c < bestc) { bestc = c; best = Lz; }
+    }
+    if (const char *e = getenv("SEPFWI_LZ")) { const int v = atoi(e); if (v >= 2) best = v; }
+    int Le = std::max(4, (int)((best + 4) / edge_cost) - 4);
+    if (const char *e = getenv("SEPFWI_LZE")) { const int v = atoi(e); if (v >= 2) Le = v; }
+    if (const char *e = getenv("SEPFWI_FORCE")) sa.force = atoi(e);
+    std::vector<int4> edge, inner;
+    auto split = [&](int z0, int z1, int L, int sx, bool is_edge) {
+        const int n = (z1 - z0 + L - 1) / L;
+        for (int c = 0; c < n; c++) {       // equal pieces
+            const int a0 = z0 + (int)((long long)(z1 - z0) * c / n), a1 = z0 + (int)((long long)(z1 - z0) * (c + 1) / n);
+            (is_edge ? edge : inner).push_back(make_int4(sx * SW_OWN, a0, a1, is_edge ? 1 : 0));
+        }
+    };
+    for (int sx = 0; sx < nStrips; sx++) { split(0, zi0, Le, sx, true); split(zi1, d.nzA, Le, sx, true); }
+    for (int sx = 0; sx < nStrips; sx++) {
+        if (strip_inner(sx)) split(zi0, zi1, best, sx, false);
+        else split(zi0, zi1, Le, sx, true);
+    }
+    // interior items: chunk-major so that concurrently running warps read neighbouring strips of the same rows
+    std::stable_sort(inner.begin(), inner.end(), [](const int4 &p, const int4 &q) { return p.y < q.y; });
+    edge.insert(edge.end(), inner.begin(), inner.end());
+    if (edge.size() > h->work_cap) {
+        if (h->work) cudaFree(h->work);
+        h->work = nullptr; h->work_cap = 0;
+        CU(cudaMalloc((void **)&h->work, edge.size() * sizeof(int4)));
+        h->work_cap = edge.size();
+    }
+    CU(cudaMemcpy(h->work, edge.data(), edge.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    sa.work = h->work; sa.nWork = (int)edge.size();
+    return 0;
+}
+
 // Forward time loop of one batch.  CPML flavour: libCUFD.cu:268-332; sponge: elasticSolver.py:241-276.
 static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_ring, cudaStream_t st)
 {
@@ -560,7 +645,22 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
     dim3 blk(BX, BY), grd((d.nx + BX - 1) / BX, (d.nzA + BY - 1) / BY, nb);
     dim3 rgrd((mrec + 127) / 128, nb), ringgrd((d.ringLen + 255) / 256, nb);
     CU(cudaEventRecord(h->ev[0], st));
-    if (h->fused) {
+    if (h->stream) {
+        StreamArgs sa;
+        int rc = stream_plan(h, nb, sa);
+        if (rc) return rc;
+        sa.fiber = h->p.fiber; sa.save_ring = save_ring ? 1 : 0; sa.nrecMax = mrec;
+        const int items = (mrec > 0 ? mrec : 0) + (save_ring ? d.ringLen : 0);
+        sa.nAux = items > 0 ? std::min(64, (items + SW_NT * 8 - 1) / (SW_NT * 8)) : 0;
+        dim3 sgrd(sa.nAux + (sa.nWork + SW_WPB - 1) / SW_WPB, nb);
+        for (int it = 0; it <= d.nSteps - 2; it++) {
+            const bool pr = it < h->prof_steps;
+            sa.it = it; sa.mask = (it >= 1 && mrec > 0) ? mask : 0;
+            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (k_stream_fwd<<<sgrd, SW_NT, 0, st>>>(a, sa)));
+        }
+        const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state
+        if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, false, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, d.nSteps - 1, mask, h->p.fiber, par)));
+    } else if (h->fused) {
         dim3 fgrd(h->ntx, h->ntz, nb);
         for (int it = 0; it <= d.nSteps - 2; it++) {
             const bool pr = it < h->prof_steps;
