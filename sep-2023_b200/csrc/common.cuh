@@ -79,6 +79,10 @@ struct SlotTab {
     // injection targets bucketed by tile INCLUDING its 2-cell halo (a target may sit in up to 4 tiles):
     // tileInjPtr[slot][nTiles+1], tileInj[slot][4*maxInj] -> index into injCell/injField/injPtr
     const int *tileInjPtr, *tileInj;
+    // injection targets bucketed for the streaming kernels: per 120-column strip (4-column halo included, so a target
+    // may sit in two strips) a row CSR  sInjPtr[slot][strip][nzA+1] into  sInj[slot][2*maxInj] -> target index
+    const int *sInjPtr, *sInj;
+    int nStrips;
 };
 
 struct KArgs {
@@ -88,6 +92,7 @@ struct KArgs {
     const float *cz;     // [NCOEF][nzA]
     const float *cx;     // [NCOEF][nx]
     const float *cxs;    // [NCOEF][ldx] x profiles for the stress-side CPML, neutral (1/K = 1, a = b = 0) outside x < nPml || x > nx-nPml-1
+    const float *cxa;    // [NCOEF][ldx] the plain x profiles at pitch ldx (adjoint sweep; 1/K = 1, a = b = 0 beyond nx)
     const float *cxv;    // [NCOEF][ldx] same for the velocity side: neutral outside x < nPml || x > nx-nPml (el_velocity.cu:56,71)
     const float *damp;   // sponge flavour: [fsz] multiplicative profile (NULL otherwise)
     float *ring;         // [slot][NFIELD][nSteps][ringLen]

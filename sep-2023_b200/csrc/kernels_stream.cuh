@@ -52,6 +52,14 @@ __device__ __forceinline__ float4 ldq_c(const float *p) { return __ldg(reinterpr
 __device__ __forceinline__ float4 ldq_rw(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void stq(float *p, const float4 &v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ float4 mk4(const float v[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
+// store only the columns of a halo lane whose stencil window is complete (lane 0: comps 2,3 ; lane 31: comps 0,1):
+// the other half of the quad belongs to the neighbouring warp, which may be writing different (newer) values
+__device__ __forceinline__ void stq_halo(float *p, const float v[4], int lane)
+{
+    if (lane == 0) *reinterpret_cast<float2 *>(p + 2) = make_float2(v[2], v[3]);
+    else if (lane == 31) *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    else *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
 __device__ __forceinline__ float sh_l(float v) { return __shfl_up_sync(0xffffffffu, v, 1); }     // value held by lane-1
 __device__ __forceinline__ float sh_r(float v) { return __shfl_down_sync(0xffffffffu, v, 1); }   // value held by lane+1
 // 7-value x windows of a quad q: backward differences need f[x-2 .. x+4], forward differences f[x-1 .. x+5]
@@ -403,6 +411,395 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_fwd(const KArgs a, co
     const int lane = threadIdx.x & 31;
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_fwd_body<false>(a, sa, s, wk, lane);
     else stream_fwd_edge(a, sa, s, wk, lane);
+}
+
+// ================================================================================================
+// adjoint sweep  adj(it+1) -> adj(it)   [adjoint buffer pa -> pa^1]
+//   phase A (row r)   adjoint velocities from the old adjoint stresses, their CPML memory, residual injection
+//   phase B (row r-2) adjoint stresses from the new adjoint velocities (register windows), their CPML memory
+// el_velocity_adj.cu:22-108, el_stress_adj.cu:22-104, res_injection_exx/_ezz utilities.cu:605-641,
+// source_grad utilities.cu:719-730 (stf gradient: done by the leading CTA from the old state).
+struct AdjCtx {
+    const float *g, *m, *psrc, *cxa, *cz, *res;
+    float *o, *pdst;
+    const int *injPtr;       // this strip's row CSR of injection targets: injPtr[z] .. injPtr[z+1]
+    const int *injList;      // -> index into injCell / injField / injPtr of the slot tables
+    const SlotTab *t;
+    float *stage;            // per-warp shared staging row: [2][128] floats (vz, vx increments by column)
+    size_t fsz, tb, cb;
+    int ld, nzA, nx, nPml, zc0, zc1, xq0, lane, s, nSteps;
+    unsigned amask;
+    bool lown, colok, anyinj;
+    bool xpl, xsl, xany;     // lane's quad touches the x CPML strip (nPml wide) / the kept strip (nPml + 2 wide); any lane of the warp does
+    float c1z, c2z, c1x, c2x, dt;
+};
+struct AdjWin {
+    float4 sz[6], sx[6], sxz[6];      // old adjoint stresses, rows r-2 .. r+3
+    float4 vz[6], vx[6];              // new adjoint velocities, rows r-4 .. r
+    float4 ovz[2], ovx[2], lam[2], mu[2], mua[2], bya[2], byb[2];
+};
+
+// residual injection into the freshly updated adjoint velocities of row r (all 128 columns of the warp)
+__device__ __forceinline__ void stream_adj_inject(const AdjCtx &k, const int r, float nvz[4], float nvx[4])
+{
+    if (r < 0 || r >= k.nzA) return;
+    const int k0 = k.injPtr[r], k1 = k.injPtr[r + 1];
+    if (k1 <= k0) return;
+    const SlotTab &t = *k.t;
+    float *sg = k.stage;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4 *>(sg + 4 * k.lane) = zero;
+    *reinterpret_cast<float4 *>(sg + 128 + 4 * k.lane) = zero;
+    __syncwarp();
+    const int xbase = k.xq0 - 4 * k.lane;      // column of lane 0, component 0
+    for (int j = k0 + k.lane; j < k1; j += 32) {
+        const int mi = k.injList[j];
+        const int cell = t.injCell[k.tb + mi];
+        const int x = cell - r * k.ld;
+        const int p0 = t.injPtr[(size_t)k.s * (t.maxInj + 1) + mi], p1 = t.injPtr[(size_t)k.s * (t.maxInj + 1) + mi + 1];
+        float v = 0.f;
+        for (int p = p0; p < p1; p++) v += t.injCoef[k.cb + p] * k.res[(size_t)t.injRec[k.cb + p] * k.nSteps];
+        sg[(t.injField[k.tb + mi] == F_VZ ? 0 : 128) + (x - xbase)] = v;
+    }
+    __syncwarp();
+    const float4 dz = *reinterpret_cast<const float4 *>(sg + 4 * k.lane), dx = *reinterpret_cast<const float4 *>(sg + 128 + 4 * k.lane);
+    nvz[0] += dz.x; nvz[1] += dz.y; nvz[2] += dz.z; nvz[3] += dz.w;
+    nvx[0] += dx.x; nvx[1] += dx.y; nvx[2] += dx.z; nvx[3] += dx.w;
+    __syncwarp();
+}
+
+template <bool EDGE, int U>
+__device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const int r)
+{
+    const int ld = k.ld, nzA = k.nzA;
+    const size_t fsz = k.fsz;
+    const float c1z = k.c1z, c2z = k.c2z, c1x = k.c1x, c2x = k.c2x, dt = k.dt;
+    constexpr int u = U;
+    constexpr int cb = u & 1, nb = cb ^ 1;
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };
+    if (!EDGE) {
+        const size_t r3 = rowoff(r + 3), r1 = rowoff(r + 1), rq = rowoff(r - 1);
+        w.sz[(u + 5) % 6] = ldq(k.g + F_SZZ * fsz + r3); w.sx[(u + 5) % 6] = ldq(k.g + F_SXX * fsz + r3); w.sxz[(u + 5) % 6] = ldq(k.g + F_SXZ * fsz + r3);
+        w.ovz[nb] = ldq(k.g + F_VZ * fsz + r1); w.ovx[nb] = ldq(k.g + F_VX * fsz + r1);
+        w.lam[nb] = ldq(k.m + M_LAM * fsz + r1); w.mu[nb] = ldq(k.m + M_MU * fsz + r1); w.mua[nb] = ldq(k.m + M_MUAVE * fsz + r1);
+        w.bya[nb] = ldq(k.m + M_BYCA * fsz + rq); w.byb[nb] = ldq(k.m + M_BYCB * fsz + rq);
+    } else {
+        const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
+        w.sz[(u + 4) % 6] = ldq(k.g + F_SZZ * fsz + r2); w.sx[(u + 4) % 6] = ldq(k.g + F_SXX * fsz + r2); w.sxz[(u + 4) % 6] = ldq(k.g + F_SXZ * fsz + r2);
+        w.ovz[cb] = ldq(k.g + F_VZ * fsz + r0); w.ovx[cb] = ldq(k.g + F_VX * fsz + r0);
+        w.lam[cb] = ldq(k.m + M_LAM * fsz + r0); w.mu[cb] = ldq(k.m + M_MU * fsz + r0); w.mua[cb] = ldq(k.m + M_MUAVE * fsz + r0);
+        w.bya[cb] = ldq(k.m + M_BYCA * fsz + rq); w.byb[cb] = ldq(k.m + M_BYCB * fsz + rq);
+    }
+    // ---- phase A: adjoint velocities at row r from the old adjoint stresses, rows r-2 .. r+2 (slots u .. u+4)
+    {
+        const float4 z1 = w.sz[(u + 1) % 6], z2 = w.sz[(u + 2) % 6], z3 = w.sz[(u + 3) % 6], z4 = w.sz[(u + 4) % 6];
+        const float4 x1 = w.sx[(u + 1) % 6], x2 = w.sx[(u + 2) % 6], x3 = w.sx[(u + 3) % 6], x4 = w.sx[(u + 4) % 6];
+        const float4 q0 = w.sxz[u % 6], q1 = w.sxz[(u + 1) % 6], q2 = w.sxz[(u + 2) % 6], q3 = w.sxz[(u + 3) % 6];
+        const float wzz[7] = XWIN_F(z2), wxx[7] = XWIN_F(x2), wxz[7] = XWIN_B(q2);
+        const float zm1[4] = Q4(z1), zc0[4] = Q4(z2), zp1[4] = Q4(z3), zp2[4] = Q4(z4);
+        const float xm1[4] = Q4(x1), xc0[4] = Q4(x2), xp1[4] = Q4(x3), xp2[4] = Q4(x4);
+        const float m2[4] = Q4(q0), m1[4] = Q4(q1), c0[4] = Q4(q2), p1[4] = Q4(q3);
+        const float l[4] = Q4(w.lam[cb]), mm[4] = Q4(w.mu[cb]), ma[4] = Q4(w.mua[cb]);
+        const float ovz[4] = Q4(w.ovz[cb]), ovx[4] = Q4(w.ovx[cb]);
+        float nvz[4], nvx[4];
+        const bool rown = (r >= k.zc0) && (r < k.zc1);
+        const size_t ro = (size_t)r * ld;
+        if (!EDGE) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float l2u = l[c] + 2.0f * mm[c];
+                const float accx = (l[c] * -DX7(wzz, c) + l2u * -DX7(wxx, c)) * dt + ma[c] * -DZ4(m2[c], m1[c], c0[c], p1[c]) * dt;
+                const float accz = (l2u * -DZ4(zm1[c], zc0[c], zp1[c], zp2[c]) + l[c] * -DZ4(xm1[c], xc0[c], xp1[c], xp2[c])) * dt + ma[c] * -DX7(wxz, c) * dt;
+                nvx[c] = ovx[c] + accx; nvz[c] = ovz[c] + accz;
+            }
+        } else {
+            // CPML rows / strips, vectorised: quads + shuffles for the x stencils of the memory variables, four row quads
+            // for the z stencils (re-read through L1).  a = 0 and 1/K = 1 outside the strips, so no per-cell branches.
+            const bool rowact = (r >= 2 && r <= nzA - 3);
+            float rKz = 1.f, az = 0.f, rKzh = 1.f, azh = 0.f, bz = 0.f, bzh = 0.f;
+            const bool zp = rowact && ((r < k.nPml) || (r > nzA - k.nPml - 1));
+            if (rowact) {
+                const float *cz = k.cz + r;
+                rKz = cz[C_RK * nzA]; az = cz[C_A * nzA]; rKzh = cz[C_RKH * nzA]; azh = cz[C_AH * nzA]; bz = cz[C_B * nzA]; bzh = cz[C_BH * nzA];
+            }
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool xl = rowact && k.xpl;                     // this lane's quad touches the x strip (nPml wide)
+            const float4 e0 = ldq_c(k.cxa + C_RK * ld), e1 = ldq_c(k.cxa + C_A * ld), e2 = ldq_c(k.cxa + C_RKH * ld), e3 = ldq_c(k.cxa + C_AH * ld);
+            const float rKx[4] = Q4(e0), ax[4] = Q4(e1), rKxh[4] = Q4(e2), axh[4] = Q4(e3);
+            float dpx[4] = {0.f, 0.f, 0.f, 0.f}, dpz[4] = {0.f, 0.f, 0.f, 0.f};     // a-weighted stencils of the old memory variables
+            if (k.xany) {      // warp-uniform: shuffles inside
+                const bool xld = rowact && k.xsl;      // the stencils reach two columns into the kept strip (nPml + 2 wide)
+                const float4 pa = xld ? ldq(k.psrc + (size_t)P_VX_X * fsz + ro) : zero4, pb = xld ? ldq(k.psrc + (size_t)P_VZ_X * fsz + ro) : zero4;
+                const float wa[7] = XWIN_F(pa), wb[7] = XWIN_B(pb);
+#pragma unroll
+                for (int c = 0; c < 4; c++) { dpx[c] = ax[c] * -DX7(wa, c); dpz[c] = axh[c] * -DX7(wb, c); }
+            }
+            if (zp) {
+                const float *pz0 = k.psrc + (size_t)P_VX_Z * fsz + ro, *pz1 = k.psrc + (size_t)P_VZ_Z * fsz + ro;
+                const float4 t0 = ldq(pz0 - 2 * ld), t1 = ldq(pz0 - ld), t2 = ldq(pz0), t3 = ldq(pz0 + ld);
+                const float4 s0 = ldq(pz1 - ld), s1 = ldq(pz1), s2 = ldq(pz1 + ld), s3 = ldq(pz1 + 2 * ld);
+                const float a0[4] = Q4(t0), a1[4] = Q4(t1), a2[4] = Q4(t2), a3[4] = Q4(t3), b0[4] = Q4(s0), b1[4] = Q4(s1), b2[4] = Q4(s2), b3[4] = Q4(s3);
+#pragma unroll
+                for (int c = 0; c < 4; c++) { dpx[c] += azh * -DZ4(a0[c], a1[c], a2[c], a3[c]); dpz[c] += az * -DZ4(b0[c], b1[c], b2[c], b3[c]); }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                nvx[c] = ovx[c]; nvz[c] = ovz[c];
+                if (rowact && ((k.amask >> c) & 1u)) {
+                    const float l2u = l[c] + 2.0f * mm[c];
+                    const float accx = (l[c] * -DX7(wzz, c) + l2u * -DX7(wxx, c)) * rKx[c] * dt + ma[c] * rKzh * -DZ4(m2[c], m1[c], c0[c], p1[c]) * dt + dpx[c];
+                    const float accz = (l2u * -DZ4(zm1[c], zc0[c], zp1[c], zp2[c]) + l[c] * -DZ4(xm1[c], xc0[c], xp1[c], xp2[c])) * rKz * dt + ma[c] * rKxh[c] * -DX7(wxz, c) * dt + dpz[c];
+                    nvx[c] = ovx[c] + accx; nvz[c] = ovz[c] + accz;
+                }
+            }
+            // CPML memory of the adjoint velocities (strips only, from the velocities BEFORE the injection).  Written for every
+            // column whose stencil window is complete (lane 0 comps 2,3 .. lane 31 comps 0,1): phase B reads them back, and the
+            // neighbouring warps that recompute the same halo cells write the same values.
+            if (xl || zp) {
+                const float4 bar4 = ldq(k.m + M_BYCA * fsz + ro), bbr4 = ldq(k.m + M_BYCB * fsz + ro);
+                const float bar[4] = Q4(bar4), bbr[4] = Q4(bbr4);
+                unsigned vm = k.amask;                               // columns with a complete window that are active
+                if (k.lane == 0) vm &= 0xcu;
+                if (k.lane == 31) vm &= 0x3u;
+                if (!k.colok) vm = 0;
+                if (xl && vm) {
+                    const float4 f0 = ldq_c(k.cxa + C_BH * ld), f1 = ldq_c(k.cxa + C_B * ld);
+                    const float bxh[4] = Q4(f0), bx[4] = Q4(f1);
+                    const float4 o0 = ldq(k.psrc + (size_t)P_SXX_X * fsz + ro), o1 = ldq(k.psrc + (size_t)P_SXZ_X * fsz + ro);
+                    float n0[4] = Q4(o0), n1[4] = Q4(o1);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int x = k.xq0 + c;
+                        if (((vm >> c) & 1u) && ((x < k.nPml) || (x > k.nx - k.nPml - 1))) {
+                            n0[c] = bxh[c] * n0[c] + bbr[c] * nvx[c] * dt;
+                            n1[c] = bx[c] * n1[c] + bar[c] * nvz[c] * dt;
+                        }
+                    }
+                    stq_halo(k.pdst + (size_t)P_SXX_X * fsz + ro, n0, k.lane); stq_halo(k.pdst + (size_t)P_SXZ_X * fsz + ro, n1, k.lane);
+                }
+                if (zp && vm) {
+                    const float4 o0 = ldq(k.psrc + (size_t)P_SXZ_Z * fsz + ro), o1 = ldq(k.psrc + (size_t)P_SZZ_Z * fsz + ro);
+                    float n0[4] = Q4(o0), n1[4] = Q4(o1);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if ((vm >> c) & 1u) {
+                            n0[c] = bz * n0[c] + bbr[c] * nvx[c] * dt;
+                            n1[c] = bzh * n1[c] + bar[c] * nvz[c] * dt;
+                        }
+                    stq_halo(k.pdst + (size_t)P_SXZ_Z * fsz + ro, n0, k.lane); stq_halo(k.pdst + (size_t)P_SZZ_Z * fsz + ro, n1, k.lane);
+                }
+            }
+        }
+        if (k.anyinj) stream_adj_inject(k, r, nvz, nvx);
+        const float4 rvz = mk4(nvz), rvx = mk4(nvx);
+        w.vz[u % 6] = rvz; w.vx[u % 6] = rvx;              // new adjoint velocity row r lives in slot u
+        if (k.lown && rown) { stq(k.o + F_VZ * fsz + ro, rvz); stq(k.o + F_VX * fsz + ro, rvx); }
+    }
+    if (EDGE) __syncwarp();      // phase B reads CPML memory written by other lanes of this warp
+    // ---- phase B: adjoint stresses at row q = r-2 from v^z rows q-2..q+1, v^x rows q-1..q+2 (row r-j lives in slot u-j)
+    {
+        const int q = r - 2;
+        const float4 v0 = w.vz[(u + 2) % 6], v1 = w.vz[(u + 3) % 6], v2 = w.vz[(u + 4) % 6], v3 = w.vz[(u + 5) % 6];
+        const float4 u0 = w.vx[(u + 3) % 6], u1 = w.vx[(u + 4) % 6], u2 = w.vx[(u + 5) % 6], u3 = w.vx[u % 6];
+        const float wvz[7] = XWIN_F(v2), wvx[7] = XWIN_B(u1);
+        const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
+        const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
+        const float ozz[4] = Q4(w.sz[u % 6]), oxx[4] = Q4(w.sx[u % 6]), oxz[4] = Q4(w.sxz[u % 6]);     // old stresses of row r-2 live in slot u
+        const float ba[4] = Q4(w.bya[cb]), bb[4] = Q4(w.byb[cb]);
+        float nzz[4], nxz[4], nxx[4];
+        const bool qown = (q >= k.zc0) && (q < k.zc1);
+        const size_t ro = (size_t)q * ld;
+        if (!EDGE) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float mdxf_vz = -DX7(wvz, c), mdzf_vx = -DZ4(vxm1[c], vxc[c], vxp1[c], vxp2[c]);
+                const float mdxb_vx = -DX7(wvx, c), mdzb_vz = -DZ4(vzm2[c], vzm1[c], vzc[c], vzp1[c]);
+                nxz[c] = oxz[c] + (mdxf_vz * ba[c] * dt + mdzf_vx * bb[c] * dt);
+                nxx[c] = oxx[c] + bb[c] * mdxb_vx * dt;
+                nzz[c] = ozz[c] + ba[c] * mdzb_vz * dt;
+            }
+        } else {
+            const bool rowact = qown && (q >= 2 && q <= nzA - 3);
+            float rKz = 1.f, az = 0.f, rKzh = 1.f, azh = 0.f, bz = 0.f, bzh = 0.f;
+            if (rowact) {
+                const float *cz = k.cz + q;
+                rKz = cz[C_RK * nzA]; az = cz[C_A * nzA]; rKzh = cz[C_RKH * nzA]; azh = cz[C_AH * nzA]; bz = cz[C_B * nzA]; bzh = cz[C_BH * nzA];
+            }
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool zpq = rowact && ((q < k.nPml) || (q > nzA - k.nPml - 1));       // rows where a_z can be non-zero
+            const bool zst = rowact && ((q < k.nPml + 2) || (q > nzA - k.nPml - 3));   // rows whose memory variables are kept
+            const bool xl2 = rowact && k.xsl && k.lown;
+            const float4 e0 = ldq_c(k.cxa + C_RK * ld), e1 = ldq_c(k.cxa + C_A * ld), e2 = ldq_c(k.cxa + C_RKH * ld), e3 = ldq_c(k.cxa + C_AH * ld);
+            const float rKx[4] = Q4(e0), ax[4] = Q4(e1), rKxh[4] = Q4(e2), axh[4] = Q4(e3);
+            float dxz[4] = {0.f, 0.f, 0.f, 0.f}, dxx[4] = {0.f, 0.f, 0.f, 0.f}, dzz[4] = {0.f, 0.f, 0.f, 0.f};
+            if (k.xany) {      // x stencils of the memory variables written in phase A of this and earlier rows (plain loads: same-warp data)
+                const bool xld = rowact && k.xsl;
+                const float4 pa = xld ? ldq_rw(k.pdst + (size_t)P_SXZ_X * fsz + ro) : zero4, pb = xld ? ldq_rw(k.pdst + (size_t)P_SXX_X * fsz + ro) : zero4;
+                const float wa[7] = XWIN_F(pa), wb[7] = XWIN_B(pb);
+#pragma unroll
+                for (int c = 0; c < 4; c++) { dxz[c] = ax[c] * -DX7(wa, c); dxx[c] = axh[c] * -DX7(wb, c); }
+            }
+            if (zpq) {
+                const float *pz0 = k.pdst + (size_t)P_SXZ_Z * fsz + ro, *pz1 = k.pdst + (size_t)P_SZZ_Z * fsz + ro;
+                const float4 t0 = ldq_rw(pz0 - ld), t1 = ldq_rw(pz0), t2 = ldq_rw(pz0 + ld), t3 = ldq_rw(pz0 + 2 * ld);
+                const float4 s0 = ldq_rw(pz1 - 2 * ld), s1 = ldq_rw(pz1 - ld), s2 = ldq_rw(pz1), s3 = ldq_rw(pz1 + ld);
+                const float a0[4] = Q4(t0), a1[4] = Q4(t1), a2[4] = Q4(t2), a3[4] = Q4(t3), b0[4] = Q4(s0), b1[4] = Q4(s1), b2[4] = Q4(s2), b3[4] = Q4(s3);
+#pragma unroll
+                for (int c = 0; c < 4; c++) { dxz[c] += az * -DZ4(a0[c], a1[c], a2[c], a3[c]); dzz[c] = azh * -DZ4(b0[c], b1[c], b2[c], b3[c]); }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                nxz[c] = oxz[c]; nxx[c] = oxx[c]; nzz[c] = ozz[c];
+                if (rowact && ((k.amask >> c) & 1u)) {
+                    const float mdxf_vz = -DX7(wvz, c), mdzf_vx = -DZ4(vxm1[c], vxc[c], vxp1[c], vxp2[c]);
+                    const float mdxb_vx = -DX7(wvx, c), mdzb_vz = -DZ4(vzm2[c], vzm1[c], vzc[c], vzp1[c]);
+                    nxz[c] = oxz[c] + (mdxf_vz * rKx[c] * ba[c] * dt + mdzf_vx * rKz * bb[c] * dt + dxz[c]);
+                    nxx[c] = oxx[c] + (bb[c] * mdxb_vx * rKxh[c] * dt + dxx[c]);
+                    nzz[c] = ozz[c] + (ba[c] * mdzb_vz * rKzh * dt + dzz[c]);
+                }
+            }
+            // CPML memory of the adjoint stresses: owner-only, strips nPml + 2 wide (el_stress_adj.cu:67-72,88-95)
+            if ((xl2 || zst) && k.lown) {
+                const float4 l4 = ldq(k.m + M_LAM * fsz + ro), m4 = ldq(k.m + M_MU * fsz + ro), a4 = ldq(k.m + M_MUAVE * fsz + ro);
+                const float lq[4] = Q4(l4), mq[4] = Q4(m4), maq[4] = Q4(a4);
+                if (xl2) {
+                    const float4 f0 = ldq_c(k.cxa + C_BH * ld), f1 = ldq_c(k.cxa + C_B * ld);
+                    const float bxh[4] = Q4(f0), bx[4] = Q4(f1);
+                    const float4 o0 = ldq(k.psrc + (size_t)P_VZ_X * fsz + ro), o1 = ldq(k.psrc + (size_t)P_VX_X * fsz + ro);
+                    float n0[4] = Q4(o0), n1[4] = Q4(o1);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int x = k.xq0 + c;
+                        if (((k.amask >> c) & 1u) && ((x < k.nPml + 2) || (x > k.nx - k.nPml - 3))) {
+                            n0[c] = bxh[c] * n0[c] + nxz[c] * maq[c] * dt;
+                            n1[c] = bx[c] * n1[c] + lq[c] * nzz[c] * dt + (lq[c] + 2.0f * mq[c]) * nxx[c] * dt;
+                        }
+                    }
+                    stq(k.pdst + (size_t)P_VZ_X * fsz + ro, mk4(n0)); stq(k.pdst + (size_t)P_VX_X * fsz + ro, mk4(n1));
+                }
+                if (zst) {
+                    const float4 o0 = ldq(k.psrc + (size_t)P_VX_Z * fsz + ro), o1 = ldq(k.psrc + (size_t)P_VZ_Z * fsz + ro);
+                    float n0[4] = Q4(o0), n1[4] = Q4(o1);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if ((k.amask >> c) & 1u) {
+                            n0[c] = bzh * n0[c] + nxz[c] * maq[c] * dt;
+                            n1[c] = bz * n1[c] + (lq[c] + 2.0f * mq[c]) * nzz[c] * dt + lq[c] * nxx[c] * dt;
+                        }
+                    stq(k.pdst + (size_t)P_VX_Z * fsz + ro, mk4(n0)); stq(k.pdst + (size_t)P_VZ_Z * fsz + ro, mk4(n1));
+                }
+            }
+        }
+        if (k.lown && qown) {
+            stq(k.o + F_SZZ * fsz + ro, mk4(nzz)); stq(k.o + F_SXZ * fsz + ro, mk4(nxz)); stq(k.o + F_SXX * fsz + ro, mk4(nxx));
+        }
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, float *stage)
+{
+    const Dims &d = a.d;
+    AdjCtx k;
+    k.ld = d.ldx; k.nzA = d.nzA; k.nx = d.nx; k.nPml = d.nPml; k.fsz = d.fsz; k.lane = lane; k.s = s; k.nSteps = d.nSteps;
+    const size_t fsz = d.fsz;
+    float *st = slot_state(a, s);
+    k.xq0 = wk.x - 4 + 4 * lane;
+    k.colok = (k.xq0 >= 0) && (k.xq0 < d.ldx);
+    const int xq = k.colok ? k.xq0 : 0;
+    k.g = st + (size_t)(sa.pa ? S_ADJ1 : S_ADJ) * fsz + xq;
+    k.o = st + (size_t)(sa.pa ? S_ADJ : S_ADJ1) * fsz + xq;
+    k.psrc = st + (size_t)(sa.pa ? S_APSI1 : S_APSI) * fsz + xq;
+    k.pdst = st + (size_t)(sa.pa ? S_APSI : S_APSI1) * fsz + xq;
+    k.m = a.model + xq;
+    k.cxa = a.cxa + xq; k.cz = a.cz;
+    k.zc0 = wk.y; k.zc1 = wk.z;
+    k.lown = (lane >= 1) && (lane <= 30) && k.colok;
+    k.c1z = d.c1z; k.c2z = d.c2z; k.c1x = d.c1x; k.c2x = d.c2x; k.dt = d.dt;
+    k.t = &a.t; k.stage = stage;
+    k.tb = (size_t)s * a.t.maxInj; k.cb = (size_t)s * a.t.maxCon;
+    k.res = a.trace + ((size_t)s * d.nTrace + T_RES) * d.maxRec * d.nSteps + sa.it;
+    {   // injection targets of this strip (halo columns included), rows of phase A
+        const int strip = wk.x / SW_OWN;
+        k.injPtr = a.t.sInjPtr + ((size_t)s * a.t.nStrips + strip) * (d.nzA + 1);
+        k.injList = a.t.sInj + (size_t)s * 2 * a.t.maxInj;
+        const int ra = max(k.zc0 - 2, 0), rb = min(k.zc1 + 2, d.nzA);
+        k.anyinj = k.injPtr[rb] > k.injPtr[ra];
+    }
+    k.amask = 0xf; k.xpl = false; k.xsl = false; k.xany = false;
+    if (EDGE) {
+        k.amask = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int x = k.xq0 + c;
+            if (x >= 2 && x <= d.nx - 3) {
+                k.amask |= 1u << c;
+                if ((x < d.nPml) || (x > d.nx - d.nPml - 1)) k.xpl = true;
+                if ((x < d.nPml + 2) || (x > d.nx - d.nPml - 3)) k.xsl = true;
+            }
+        }
+        k.xany = __any_sync(0xffffffffu, k.xsl);
+    }
+    AdjWin w;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 6; j++) { w.sz[j] = w.sx[j] = w.sxz[j] = w.vz[j] = w.vx[j] = zero; }
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), d.nzA - 1) * d.ldx; };
+#pragma unroll
+    for (int j = 0; j < (EDGE ? 4 : 5); j++) {
+        const size_t ro = rowoff(k.zc0 - 4 + j);
+        w.sz[j] = ldq(k.g + F_SZZ * fsz + ro); w.sx[j] = ldq(k.g + F_SXX * fsz + ro); w.sxz[j] = ldq(k.g + F_SXZ * fsz + ro);
+    }
+    w.ovz[0] = w.ovx[0] = w.lam[0] = w.mu[0] = w.mua[0] = w.bya[0] = w.byb[0] = zero;
+    w.ovz[1] = w.ovx[1] = w.lam[1] = w.mu[1] = w.mua[1] = w.bya[1] = w.byb[1] = zero;
+    if (!EDGE) {
+        const size_t ro = rowoff(k.zc0 - 2);
+        w.ovz[0] = ldq(k.g + F_VZ * fsz + ro); w.ovx[0] = ldq(k.g + F_VX * fsz + ro);
+        w.lam[0] = ldq(k.m + M_LAM * fsz + ro); w.mu[0] = ldq(k.m + M_MU * fsz + ro); w.mua[0] = ldq(k.m + M_MUAVE * fsz + ro);
+    }
+    const int niter = (k.zc1 - k.zc0) + 4;
+    if (!EDGE) {
+#pragma unroll 1
+        for (int kk = 0; kk < niter; kk += 6) {
+            const int r = k.zc0 - 2 + kk;
+            stream_adj_row<EDGE, 0>(k, w, r);     stream_adj_row<EDGE, 1>(k, w, r + 1); stream_adj_row<EDGE, 2>(k, w, r + 2);
+            stream_adj_row<EDGE, 3>(k, w, r + 3); stream_adj_row<EDGE, 4>(k, w, r + 4); stream_adj_row<EDGE, 5>(k, w, r + 5);
+        }
+    } else {
+#pragma unroll 1
+        for (int kk = 0; kk < niter; kk++) {
+            stream_adj_row<EDGE, 0>(k, w, k.zc0 - 2 + kk);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { w.sz[j] = w.sz[j + 1]; w.sx[j] = w.sx[j + 1]; w.sxz[j] = w.sxz[j + 1]; }
+            w.vz[2] = w.vz[3]; w.vz[3] = w.vz[4]; w.vz[4] = w.vz[5]; w.vz[5] = w.vz[0];
+            w.vx[3] = w.vx[4]; w.vx[4] = w.vx[5]; w.vx[5] = w.vx[0];
+        }
+    }
+}
+
+__device__ __forceinline__ void stream_adj_edge(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, float *stage)
+{ stream_adj_body<true>(a, sa, s, wk, lane, stage); }
+
+// grid: x = 1 + ceil(nWork / SW_WPB), y = slot ; CTA 0 writes the stf gradient
+__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, const StreamArgs sa)
+{
+    __shared__ __align__(16) float stage[SW_WPB][256];
+    const int s = blockIdx.y;
+    const Dims &d = a.d;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {      // source_grad, utilities.cu:719-730, from the adjoint state after step it+1
+            const float *src = slot_state(a, s) + (size_t)(sa.pa ? S_ADJ1 : S_ADJ) * d.fsz;
+            const size_t i = (size_t)a.t.zs[s] * d.ldx + a.t.xs[s];
+            a.gstf[(size_t)s * d.nSteps + sa.it] = -(src[(size_t)F_SZZ * d.fsz + i] + a.t.rxz[s] * src[(size_t)F_SXX * d.fsz + i]) * d.dt;
+        }
+        return;
+    }
+    const int wg = ((int)blockIdx.x - 1) * SW_WPB + ((int)threadIdx.x >> 5);
+    if (wg >= sa.nWork) return;
+    const int4 wk = __ldg(sa.work + wg);
+    const int lane = threadIdx.x & 31;
+    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_adj_body<false>(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
+    else stream_adj_edge(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
 }
 
 }  // namespace sepfwi

@@ -50,7 +50,7 @@ struct sepfwi_handle {
     int B;                 // slots
     bool sponge;
     // device arenas
-    float *state = nullptr, *model = nullptr, *cz = nullptr, *cx = nullptr, *cxs = nullptr, *cxv = nullptr, *damp = nullptr;
+    float *state = nullptr, *model = nullptr, *cz = nullptr, *cx = nullptr, *cxs = nullptr, *cxv = nullptr, *cxa = nullptr, *damp = nullptr;
     float *ring = nullptr, *trace = nullptr, *grad = nullptr, *gstf = nullptr;
     float *dense[3] = {nullptr, nullptr, nullptr};   // [nz][nx] staging for model in / gradient out
     int *maxcp = nullptr;
@@ -61,7 +61,8 @@ struct sepfwi_handle {
     size_t n_int = 0, n_flt = 0;
     SlotTab tab;
     // offsets (in elements) of the packed tables
-    size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_tilePtr, o_tileRec, o_tileInjPtr, o_tileInj;
+    size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_tilePtr, o_tileRec, o_tileInjPtr, o_tileInj, o_sInjPtr, o_sInj;
+    int nStrips = 0;
     int ntx = 0, ntz = 0;
     bool fused = false;    // tile kernels (kernels = 2); their backward half also serves kernels = 0 until the streaming one lands
     bool stream = false;   // register-streaming kernels (kernels = 0)
@@ -228,7 +229,7 @@ extern "C" int sepfwi_ring_len(const sepfwi_params *p)
 static KArgs kargs(const sepfwi_handle *h)
 {
     KArgs a;
-    a.d = h->d; a.state = h->state; a.model = h->model; a.cz = h->cz; a.cx = h->cx; a.cxs = h->cxs; a.cxv = h->cxv; a.damp = h->damp;
+    a.d = h->d; a.state = h->state; a.model = h->model; a.cz = h->cz; a.cx = h->cx; a.cxs = h->cxs; a.cxv = h->cxv; a.cxa = h->cxa; a.damp = h->damp;
     a.ring = h->ring; a.trace = h->trace; a.grad = h->grad; a.gstf = h->gstf; a.t = h->tab;
     if (!h->use_w) a.t.w = nullptr;
     return a;
@@ -238,7 +239,7 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    float *fp[] = {h->state, h->model, h->cz, h->cx, h->cxs, h->cxv, h->damp, h->ring, h->trace, h->grad, h->gstf,
+    float *fp[] = {h->state, h->model, h->cz, h->cx, h->cxs, h->cxv, h->cxa, h->damp, h->ring, h->trace, h->grad, h->gstf,
                    h->dense[0], h->dense[1], h->dense[2], h->t_flt};
     for (float *q : fp) if (q) cudaFree(q);
     if (h->maxcp) cudaFree(h->maxcp);
@@ -291,6 +292,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     ALLOC(h->cx, (size_t)NCOEF * d.nx * sizeof(float));
     ALLOC(h->cxs, (size_t)NCOEF * d.ldx * sizeof(float));
     ALLOC(h->cxv, (size_t)NCOEF * d.ldx * sizeof(float));
+    ALLOC(h->cxa, (size_t)NCOEF * d.ldx * sizeof(float));
     ALLOC(h->trace, (size_t)B * d.nTrace * d.maxRec * d.nSteps * sizeof(float));
     ALLOC(h->gstf, (size_t)B * d.nSteps * sizeof(float));
     for (int k = 0; k < 3; k++) ALLOC(h->dense[k], (size_t)d.nz * d.nx * sizeof(float));
@@ -315,6 +317,8 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     h->ntx = (d.nx + FTX - 1) / FTX; h->ntz = (d.nzA + FTZ - 1) / FTZ;
     h->o_tilePtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileRec = takei((size_t)B * d.maxRec);
     h->o_tileInjPtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileInj = takei((size_t)B * 4 * maxInj);
+    h->nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
+    h->o_sInjPtr = takei((size_t)B * h->nStrips * (d.nzA + 1)); h->o_sInj = takei((size_t)B * 2 * maxInj);
     h->n_int = oi;
     h->stream = !h->sponge && pp->kernels == 0;
     h->fused = !h->sponge && (pp->kernels == 0 || pp->kernels == 2);
@@ -348,6 +352,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     t.maxInj = maxInj; t.maxCon = maxCon;
     t.tilePtr = h->t_int + h->o_tilePtr; t.tileRec = h->t_int + h->o_tileRec; t.nTiles = h->ntx * h->ntz; t.ntx = h->ntx;
     t.tileInjPtr = h->t_int + h->o_tileInjPtr; t.tileInj = h->t_int + h->o_tileInj;
+    t.sInjPtr = h->t_int + h->o_sInjPtr; t.sInj = h->t_int + h->o_sInj; t.nStrips = h->nStrips;
 
     // CPML profiles / sponge
     if (!h->sponge) {
@@ -360,7 +365,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         CU(cudaMemcpy(h->cz, h->hcz.data(), (size_t)NCOEF * d.nzA * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->cx, h->hcx.data(), (size_t)NCOEF * d.nx * sizeof(float), cudaMemcpyHostToDevice));
         // quad-aligned copies for the streaming kernels, neutral wherever the reference kernel skips the CPML branch
-        std::vector<float> ts((size_t)NCOEF * d.ldx), tv((size_t)NCOEF * d.ldx);
+        std::vector<float> ts((size_t)NCOEF * d.ldx), tv((size_t)NCOEF * d.ldx), ta((size_t)NCOEF * d.ldx);
         for (int x = 0; x < d.ldx; x++) {
             const bool ins = x < d.nx && ((x < d.nPml) || (x > d.nx - d.nPml - 1));     // el_stress.cu:63
             const bool inv = x < d.nx && ((x < d.nPml) || (x > d.nx - d.nPml));         // el_velocity.cu:56,71
@@ -368,10 +373,12 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
                 const float neutral = (k == C_RK || k == C_RKH) ? 1.0f : 0.0f;
                 ts[(size_t)k * d.ldx + x] = ins ? h->hcx[(size_t)k * d.nx + x] : neutral;
                 tv[(size_t)k * d.ldx + x] = inv ? h->hcx[(size_t)k * d.nx + x] : neutral;
+                ta[(size_t)k * d.ldx + x] = x < d.nx ? h->hcx[(size_t)k * d.nx + x] : neutral;
             }
         }
         CU(cudaMemcpy(h->cxs, ts.data(), ts.size() * sizeof(float), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->cxv, tv.data(), tv.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->cxa, ta.data(), ta.size() * sizeof(float), cudaMemcpyHostToDevice));
     } else {
         // multiplicative sponge sin^2(pi/2 i/ndamp) from all four sides, elasticSolver.py:74-79
         std::vector<float> dm(d.fsz, 1.0f);
@@ -555,6 +562,26 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
             for (int t = 0; t < nT; t++) tp[t + 1] += tp[t];
             std::vector<int> cur(tp, tp + nT);
             for (int m = 0; m < nt; m++) for_tiles(m, [&](int t) { tl[cur[t]++] = m; });
+            // ... and by streaming strip (columns [120 k - 4, 120 k + 124)) and row
+            const int nS = h->nStrips, nR = d.nzA + 1;
+            int *sp = h->h_int + h->o_sInjPtr + (size_t)s * nS * nR, *sl = h->h_int + h->o_sInj + (size_t)s * 2 * maxInj;
+            std::fill(sp, sp + (size_t)nS * nR, 0);
+            auto for_strips = [&](int m, auto &&fn) {
+                const int z = cell[m] / d.ldx, x = cell[m] % d.ldx;
+                for (int k = std::max(0, (x - 124) / SW_OWN); k < nS && k * SW_OWN - 4 <= x; k++)
+                    if (x >= k * SW_OWN - 4 && x < k * SW_OWN + SW_OWN + 4) fn(k, z);
+            };
+            // counting sort over (strip, row); entry [k][z] first holds the count of row z-1 ... then the running offset
+            std::vector<int> cnt((size_t)nS * d.nzA, 0);
+            for (int m = 0; m < nt; m++) for_strips(m, [&](int k, int z) { cnt[(size_t)k * d.nzA + z]++; });
+            int run = 0;
+            for (int k = 0; k < nS; k++) {
+                for (int z = 0; z < d.nzA; z++) { sp[(size_t)k * nR + z] = run; run += cnt[(size_t)k * d.nzA + z]; }
+                sp[(size_t)k * nR + d.nzA] = run;
+            }
+            std::vector<int> cur2((size_t)nS * d.nzA);
+            for (int k = 0; k < nS; k++) for (int z = 0; z < d.nzA; z++) cur2[(size_t)k * d.nzA + z] = sp[(size_t)k * nR + z];
+            for (int m = 0; m < nt; m++) for_strips(m, [&](int k, int z) { sl[cur2[(size_t)k * d.nzA + z]++] = m; });
         }
     }
     for (int s = nb; s < h->B; s++) {
@@ -562,6 +589,7 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
         const int nT = h->ntx * h->ntz;
         std::fill(h->h_int + h->o_tilePtr + (size_t)s * (nT + 1), h->h_int + h->o_tilePtr + (size_t)(s + 1) * (nT + 1), 0);
         std::fill(h->h_int + h->o_tileInjPtr + (size_t)s * (nT + 1), h->h_int + h->o_tileInjPtr + (size_t)(s + 1) * (nT + 1), 0);
+        std::fill(h->h_int + h->o_sInjPtr + (size_t)s * h->nStrips * (d.nzA + 1), h->h_int + h->o_sInjPtr + (size_t)(s + 1) * h->nStrips * (d.nzA + 1), 0);
     }
     CU(cudaMemcpyAsync(h->t_int, h->h_int, h->n_int * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->t_flt, h->h_flt, h->n_flt * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -585,10 +613,12 @@ static int stream_plan(sepfwi_handle *h, int nb, StreamArgs &sa)
     const Dims &d = h->d;
     memset(&sa, 0, sizeof(sa));
     const int nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
-    const int zi0 = d.nPml + 2, zi1 = d.nzA - d.nPml - 2;      // interior rows [zi0, zi1)
+    // interior rows [zi0, zi1) / strips: the adjoint sweep keeps CPML memory on strips nPml + 2 wide (el_stress_adj.cu:67-72),
+    // and a warp recomputes a 2-cell halo, so the branch-free variant needs a margin of nPml + 4
+    const int zi0 = d.nPml + 4, zi1 = d.nzA - d.nPml - 4;
     const double conc = (double)h->nSM * 2 * SW_WPB;
     const double edge_cost = 1.8;
-    auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml && x0 + SW_OWN + 3 <= d.nx - d.nPml - 1; };
+    auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 2 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 3; };
     int nInnerStrips = 0;
     for (int sx = 0; sx < nStrips; sx++) nInnerStrips += strip_inner(sx) ? 1 : 0;
     int best = 8;
@@ -743,8 +773,11 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     dim3 rgrd((rx + BX - 1) / BX, (rz + BY - 1) / BY, nb);
     dim3 igrd((minj + 127) / 128, nb);
     CU(cudaEventRecord(h->ev[2], st));
+    StreamArgs sa;
+    if (h->stream) { int rc = stream_plan(h, nb, sa); if (rc) return rc; }
     if (h->fused) {
         dim3 agrd(h->ntx, h->ntz, nb);
+        dim3 sagrd(1 + (sa.nWork + SW_WPB - 1) / SW_WPB, nb);
         const int xbase = (d.nPml - 2) & ~3;
         dim3 cgrd((d.x1 + 2 - xbase) / FTX + 1, (d.z1 + 2 - (d.nPml - 2)) / FTZ + 1, nb);
         int q = (d.nSteps - 1) & 1, pa = 0;     // forward state nSteps-1 sits in buffer q; adjoint starts in buffer 0
@@ -753,6 +786,10 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
             FusedBwdArgs fa;
             fa.it = it; fa.q = q; fa.pa = pa;
             LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F4_NT, R_SMEM, st>>>(a, fa)));
+            if (h->stream) {
+                sa.it = it; sa.q = q; sa.pa = pa;
+                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (k_stream_adj<<<sagrd, SW_NT, 0, st>>>(a, sa)));
+            } else
             LAUNCH(h, SEPFWI_K_FUSED_ADJ, pr, st, (k_fused_adj<<<agrd, F4_NT, A_SMEM, st>>>(a, fa)));
             q ^= 1; pa ^= 1;
         }

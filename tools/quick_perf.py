@@ -42,14 +42,14 @@ def run(name, batch, grad, nsteps, profile=False):
         if profile:
             pr = P.profile()
             print("     per-kernel us:", {k: round(1e3 * ms / n, 1) for k, (ms, n) in pr.items()})
-            fk = [k for k in ("fused_fwd", "stress_fwd", "velocity_fwd") if k in pr]
-            bk = [k for k in ("fused_recon", "fused_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in pr]
+            fk = [k for k in ("stream_fwd", "fused_fwd", "stress_fwd", "velocity_fwd") if k in pr]
+            bk = [k for k in ("stream_recon", "stream_adj", "fused_recon", "fused_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in pr]
             tf = sum(pr[k][0] / pr[k][1] for k in fk) * 1e-3
-            print("     forward step: %.1f us -> %.0f GB/s algorithmic (52 B/cell) = %.2f of 6541" % (tf * 1e6, 52 * w["live"] / tf / 1e9, 52 * w["live"] / tf / 1e9 / 6541.5))
+            print("     forward step: %.1f us -> %.0f GB/s algorithmic (52 B/cell) = %.2f of 6451" % (tf * 1e6, 52 * w["live"] / tf / 1e9, 52 * w["live"] / tf / 1e9 / 6451.2))
             if bk:
                 tb = sum(pr[k][0] / pr[k][1] for k in bk) * 1e-3
                 ab = (52 * w["live"] + 64 * w["interior"]) / tb / 1e9
-                print("     backward step: %.1f us -> %.0f GB/s algorithmic = %.2f of 6541" % (tb * 1e6, ab, ab / 6541.5))
+                print("     backward step: %.1f us -> %.0f GB/s algorithmic = %.2f of 6451" % (tb * 1e6, ab, ab / 6451.2))
 
 
 print("lib:", os.environ.get("SEPFWI_LIB", "default"), "kernels", kernels)
