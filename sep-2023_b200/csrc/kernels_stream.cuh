@@ -24,6 +24,8 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_base.cuh"
+#include "kernels_fused.cuh"      // tile_touches_ring_ext
+#include "kernels_fused_bwd.cuh"  // interior()
 
 namespace sepfwi {
 
@@ -800,6 +802,286 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, co
     const int lane = threadIdx.x & 31;
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_adj_body<false>(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
     else stream_adj_edge(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
+}
+
+// ================================================================================================
+// reverse-time reconstruction + imaging   fwd(it+1) -> fwd(it)   [forward buffer q -> q^1], gradients += ...
+//   stage 1 (row r)    v(it) = v - D(sigma) b dt on the interior, ring restore; density imaging terms ga, gb and the
+//                      grho gather (rows r, r-1 / columns x, x-1)                       el_velocity.cu:84-117, to_bnd
+//   stage 2 (row r-2)  sigma(it) = sigma - amp[src] - C D(v(it)) dt, ring restore; glam, gmu (normal part + the four-point
+//                      shear spray of el_stress.cu:112-123 evaluated as a gather over rows r-2, r-3 / columns x, x-1)
+// Same march as the other two kernels, but 18 operand quads per row: they are prefetched through a per-warp
+// shared-memory ring with cp.async (each lane copies and later reads only its own 16 bytes, so a cp.async.wait_group
+// is the only synchronisation) -- the registers hold just the stencil windows.
+constexpr int RC_NARR = 18;
+constexpr int RC_NST = 3;                                   // ring stages: operands are requested RC_NST-1 rows ahead
+constexpr int RC_WARP_BYTES = RC_NST * RC_NARR * 512;       // 27 KB per warp
+constexpr size_t RC_SMEM = (size_t)SW_WPB * RC_WARP_BYTES;  // 108 KB per CTA, 2 CTAs per SM
+enum { RA_SZZ = 0, RA_SXZ, RA_SXX, RA_OVZ, RA_OVX, RA_AVZ, RA_AVX, RA_BA, RA_BB, RA_GR,      // rows r+2, r+1, r, then row r
+       RA_ASZZ, RA_ASXZ, RA_ASXX, RA_LAM, RA_MU, RA_MUA, RA_GL, RA_GM };                        // row r-2
+
+__device__ __forceinline__ void cp16(unsigned saddr, const float *g)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g)); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds4(unsigned saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+struct RecCtx {
+    const float *g, *adj, *m, *ringb, *amp;
+    float *o, *grad;
+    unsigned ring_s;          // shared-memory address of this lane's 16 bytes in stage 0, array 0
+    size_t fsz, rfs;
+    int ld, nzA, nx, nPml, z1, x1, zc0, zc1, zs, xs, xq0;
+    bool lown, ring;
+    float c1z, c2z, c1x, c2x, dt;
+    Dims d;
+};
+struct RecWin {
+    float4 szz[6], sxz[6], sxx[6];     // old stresses (state it+1): rows r-2 .. r+2 / r+1 / r
+    float4 vz[6], vx[6];               // reconstructed velocities (state it): rows r-4 .. r
+    float ga_prev[4], sh_prev[4];      // density term of row r-1, shear term of row r-3
+};
+
+// request the operands of the iteration whose stage-1 row is r
+__device__ __forceinline__ void stream_rec_issue(const RecCtx &k, const int r, const int stage)
+{
+    const int ld = k.ld, nzA = k.nzA;
+    const size_t fsz = k.fsz;
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };
+    const size_t r2 = rowoff(r + 2), r1 = rowoff(r + 1), r0 = rowoff(r), rq = rowoff(r - 2);
+    const unsigned sb = k.ring_s + (unsigned)stage * (RC_NARR * 512);
+    cp16(sb + RA_SZZ * 512, k.g + F_SZZ * fsz + r2); cp16(sb + RA_SXZ * 512, k.g + F_SXZ * fsz + r1); cp16(sb + RA_SXX * 512, k.g + F_SXX * fsz + r0);
+    cp16(sb + RA_OVZ * 512, k.g + F_VZ * fsz + r0); cp16(sb + RA_OVX * 512, k.g + F_VX * fsz + r0);
+    cp16(sb + RA_AVZ * 512, k.adj + F_VZ * fsz + r0); cp16(sb + RA_AVX * 512, k.adj + F_VX * fsz + r0);
+    cp16(sb + RA_BA * 512, k.m + M_BYCA * fsz + r0); cp16(sb + RA_BB * 512, k.m + M_BYCB * fsz + r0);
+    cp16(sb + RA_GR * 512, k.grad + 2 * fsz + r0);
+    cp16(sb + RA_ASZZ * 512, k.adj + F_SZZ * fsz + rq); cp16(sb + RA_ASXZ * 512, k.adj + F_SXZ * fsz + rq); cp16(sb + RA_ASXX * 512, k.adj + F_SXX * fsz + rq);
+    cp16(sb + RA_LAM * 512, k.m + M_LAM * fsz + rq); cp16(sb + RA_MU * 512, k.m + M_MU * fsz + rq); cp16(sb + RA_MUA * 512, k.m + M_MUAVE * fsz + rq);
+    cp16(sb + RA_GL * 512, k.grad + 0 * fsz + rq); cp16(sb + RA_GM * 512, k.grad + 1 * fsz + rq);
+    cp_commit();
+}
+
+template <bool EDGE, int U>
+__device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const int r, const int stage)
+{
+    const int ld = k.ld;
+    const size_t fsz = k.fsz;
+    const float c1z = k.c1z, c2z = k.c2z, c1x = k.c1x, c2x = k.c2x, dt = k.dt;
+    constexpr int u = U;
+    stream_rec_issue(k, r + (RC_NST - 1), stage == 0 ? RC_NST - 1 : stage - 1);
+    cp_wait<RC_NST - 1>();
+    const unsigned sb = k.ring_s + (unsigned)stage * (RC_NARR * 512);
+    w.szz[(u + 4) % 6] = lds4(sb + RA_SZZ * 512);       // row r+2
+    w.sxz[(u + 3) % 6] = lds4(sb + RA_SXZ * 512);       // row r+1
+    w.sxx[(u + 2) % 6] = lds4(sb + RA_SXX * 512);       // row r
+    // ---- stage 1: velocities of time `it` at row r ; density imaging
+    {
+        const float4 p0 = w.szz[(u + 1) % 6], p1 = w.szz[(u + 2) % 6], p2 = w.szz[(u + 3) % 6], p3 = w.szz[(u + 4) % 6];
+        const float4 q0 = w.sxz[u % 6], q1 = w.sxz[(u + 1) % 6], q2 = w.sxz[(u + 2) % 6], q3 = w.sxz[(u + 3) % 6];
+        const float4 xc = w.sxx[(u + 2) % 6];
+        const float wxz[7] = XWIN_B(q2), wxx[7] = XWIN_F(xc);
+        const float zzm1[4] = Q4(p0), zzc[4] = Q4(p1), zzp1[4] = Q4(p2), zzp2[4] = Q4(p3);
+        const float xzm2[4] = Q4(q0), xzm1[4] = Q4(q1), xzc[4] = Q4(q2), xzp1[4] = Q4(q3);
+        const float4 ovz4 = lds4(sb + RA_OVZ * 512), ovx4 = lds4(sb + RA_OVX * 512), avz4 = lds4(sb + RA_AVZ * 512), avx4 = lds4(sb + RA_AVX * 512);
+        const float4 ba4 = lds4(sb + RA_BA * 512), bb4 = lds4(sb + RA_BB * 512);
+        const float ovz[4] = Q4(ovz4), ovx[4] = Q4(ovx4), avz[4] = Q4(avz4), avx[4] = Q4(avx4), ba[4] = Q4(ba4), bb[4] = Q4(bb4);
+        float nvz[4], nvx[4], ga[4], gb[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float A = DZ4(zzm1[c], zzc[c], zzp1[c], zzp2[c]) + DX7(wxz, c);
+            const float B = DZ4(xzm2[c], xzm1[c], xzc[c], xzp1[c]) + DX7(wxx, c);
+            const bool in = !EDGE || interior(k.d, r, k.xq0 + c);
+            nvz[c] = in ? ovz[c] - A * ba[c] * dt : ovz[c];
+            nvx[c] = in ? ovx[c] - B * bb[c] * dt : ovx[c];
+            ga[c] = in ? avz[c] * A * dt * (0.5f * ba[c] * ba[c]) : 0.f;
+            gb[c] = in ? avx[c] * B * dt * (0.5f * bb[c] * bb[c]) : 0.f;
+            if (EDGE && k.ring) {
+                int r0, r1;
+                ring_indices2(k.d, r, k.xq0 + c, r0, r1);
+                const int ri = r0 >= 0 ? r0 : r1;
+                if (ri >= 0) { nvz[c] = k.ringb[F_VZ * k.rfs + ri]; nvx[c] = k.ringb[F_VX * k.rfs + ri]; }
+            }
+        }
+        const float4 rvz = mk4(nvz), rvx = mk4(nvx);
+        w.vz[u % 6] = rvz; w.vx[u % 6] = rvx;
+        // grho gather (el_velocity.cu:104-110 sprays ga to (z,x),(z+1,x) and gb to (z,x),(z,x+1))
+        const float gbl = sh_l(gb[3]);
+        const bool rown = (r >= k.zc0) && (r < k.zc1);
+        const bool rreg = !EDGE || (r >= k.nPml - 2 && r <= k.z1 + 2 && k.xq0 + 3 >= k.nPml - 2 && k.xq0 <= k.x1 + 2);
+        if (k.lown && rown && rreg) {
+            const size_t ro = (size_t)r * ld;
+            const float4 g4 = lds4(sb + RA_GR * 512);
+            float gr[4] = Q4(g4);
+            const float gbW[5] = {gbl, gb[0], gb[1], gb[2], gb[3]};
+            const bool zle = !EDGE || (r <= k.z1);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const bool in = !EDGE || interior(k.d, r, k.xq0 + c);
+                float grr = (in ? ga[c] + gbW[c + 1] : 0.f) + gbW[c];
+                if (zle) grr += w.ga_prev[c];
+                gr[c] += grr;
+            }
+            stq(k.grad + 2 * fsz + ro, mk4(gr));
+            stq(k.o + F_VZ * fsz + ro, rvz); stq(k.o + F_VX * fsz + ro, rvx);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) w.ga_prev[c] = ga[c];
+    }
+    // ---- stage 2: stresses of time `it` at row q = r-2 ; lambda / mu imaging
+    {
+        const int q = r - 2;
+        const float4 v0 = w.vz[(u + 2) % 6], v1 = w.vz[(u + 3) % 6], v2 = w.vz[(u + 4) % 6], v3 = w.vz[(u + 5) % 6];
+        const float4 u0 = w.vx[(u + 3) % 6], u1 = w.vx[(u + 4) % 6], u2 = w.vx[(u + 5) % 6], u3 = w.vx[u % 6];
+        const float wvz[7] = XWIN_F(v2), wvx[7] = XWIN_B(u1);
+        const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
+        const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
+        const float ozz[4] = Q4(w.szz[u % 6]), oxz[4] = Q4(w.sxz[u % 6]), oxx[4] = Q4(w.sxx[u % 6]);     // old stresses of row r-2: slot u
+        const float4 za4 = lds4(sb + RA_ASZZ * 512), sa4 = lds4(sb + RA_ASXZ * 512), xa4 = lds4(sb + RA_ASXX * 512);
+        const float4 lam4 = lds4(sb + RA_LAM * 512), mu4 = lds4(sb + RA_MU * 512), mua4 = lds4(sb + RA_MUA * 512);
+        const float za[4] = Q4(za4), sa[4] = Q4(sa4), xa[4] = Q4(xa4), lam[4] = Q4(lam4), mu[4] = Q4(mu4), mua[4] = Q4(mua4);
+        float D1[4], D2[4], D3[4], sh[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            D1[c] = DZ4(vzm2[c], vzm1[c], vzc[c], vzp1[c]); D2[c] = DX7(wvx, c);
+            D3[c] = DZ4(vxm1[c], vxc[c], vxp1[c], vxp2[c]) + DX7(wvz, c);
+            // mu_ave / sum(1/mu) = mu_ave^2 / 4  (mu_ave is the 4-point harmonic mean; 0 when any corner is 0)
+            const float v = -sa[c] * D3[c] * dt * (0.25f * mua[c] * mua[c]) * 1e6f;
+            sh[c] = (!EDGE || interior(k.d, q, k.xq0 + c)) ? v : 0.f;
+        }
+        const float shl = sh_l(sh[3]), shul = sh_l(w.sh_prev[3]);
+        const bool qown = (q >= k.zc0) && (q < k.zc1);
+        const bool qreg = !EDGE || (q >= k.nPml - 2 && q <= k.z1 + 2 && k.xq0 + 3 >= k.nPml - 2 && k.xq0 <= k.x1 + 2);
+        if (k.lown && qown && qreg) {
+            const size_t ro = (size_t)q * ld;
+            const float4 g0 = lds4(sb + RA_GL * 512), g1 = lds4(sb + RA_GM * 512);
+            float gl[4] = Q4(g0), gm[4] = Q4(g1);
+            const float shW[5] = {shl, sh[0], sh[1], sh[2], sh[3]}, shUW[5] = {shul, w.sh_prev[0], w.sh_prev[1], w.sh_prev[2], w.sh_prev[3]};
+            float nzz[4], nxz[4], nxx[4];
+            const bool zle = !EDGE || (q <= k.z1);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int x = k.xq0 + c;
+                float tzz = ozz[c], txx = oxx[c], txz = oxz[c];
+                if (q == k.zs && x == k.xs) { const float amp = *k.amp; tzz -= amp; txx -= amp; }
+                const bool in = !EDGE || interior(k.d, q, x);
+                if (in) {
+                    const float l2u = lam[c] + 2.0f * mu[c];
+                    tzz -= (l2u * D1[c] + lam[c] * D2[c]) * dt;
+                    txx -= (lam[c] * D1[c] + l2u * D2[c]) * dt;
+                    txz -= mua[c] * D3[c] * dt;
+                    gl[c] += -(za[c] + xa[c]) * (D1[c] + D2[c]) * dt * 1e6f;
+                }
+                float shg = shW[c + 1] + shW[c];
+                if (zle) { shg += shUW[c + 1]; if (!EDGE || x <= k.x1) shg += shUW[c]; }
+                const float gmn = in ? (-2.0f * za[c] * D1[c] * dt - 2.0f * xa[c] * D2[c] * dt) * 1e6f : 0.f;
+                // fast division (2 ulp): the IEEE routine's slow path is taken for the zero / denormal numerators that fill most
+                // of the grid early in the reverse sweep and then costs more than the rest of the kernel
+                if (!EDGE || in || shg != 0.f) gm[c] += gmn + __fdividef(shg, mu[c] * mu[c]);
+                if (EDGE && k.ring) {
+                    int r0, r1;
+                    ring_indices2(k.d, q, x, r0, r1);
+                    const int ri = r0 >= 0 ? r0 : r1;
+                    if (ri >= 0) { tzz = k.ringb[F_SZZ * k.rfs + ri]; txz = k.ringb[F_SXZ * k.rfs + ri]; txx = k.ringb[F_SXX * k.rfs + ri]; }
+                }
+                nzz[c] = tzz; nxx[c] = txx; nxz[c] = txz;
+            }
+            stq(k.grad + 0 * fsz + ro, mk4(gl)); stq(k.grad + 1 * fsz + ro, mk4(gm));
+            stq(k.o + F_SZZ * fsz + ro, mk4(nzz)); stq(k.o + F_SXZ * fsz + ro, mk4(nxz)); stq(k.o + F_SXX * fsz + ro, mk4(nxx));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) w.sh_prev[c] = sh[c];
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, const unsigned smem_warp)
+{
+    const Dims &d = a.d;
+    RecCtx k;
+    k.d = d;
+    k.ld = d.ldx; k.nzA = d.nzA; k.nx = d.nx; k.nPml = d.nPml; k.z1 = d.z1; k.x1 = d.x1; k.fsz = d.fsz;
+    const size_t fsz = d.fsz;
+    float *st = slot_state(a, s);
+    k.xq0 = wk.x - 4 + 4 * lane;
+    const bool colok = (k.xq0 >= 0) && (k.xq0 < d.ldx);
+    const int xq = colok ? k.xq0 : 0;
+    k.g = st + (size_t)(sa.q ? S_FWD1 : S_FWD) * fsz + xq;
+    k.o = st + (size_t)(sa.q ? S_FWD : S_FWD1) * fsz + xq;
+    k.adj = st + (size_t)(sa.pa ? S_ADJ1 : S_ADJ) * fsz + xq;
+    k.m = a.model + xq;
+    k.grad = a.grad + (size_t)s * 3 * fsz + xq;
+    k.ringb = a.ring + (((size_t)s * NFIELD) * d.nSteps + sa.it) * d.ringLen;
+    k.rfs = (size_t)d.nSteps * d.ringLen;
+    k.amp = a.t.amp + (size_t)s * d.nSteps + sa.it;
+    k.zs = a.t.zs[s]; k.xs = a.t.xs[s];
+    // rows outside the region interior U ring = [nPml-2, z1+2] are never touched by the reverse sweep
+    k.zc0 = max(wk.y, d.nPml - 2); k.zc1 = min(wk.z, d.z1 + 3);
+    if (k.zc1 <= k.zc0) return;
+    if (wk.x + SW_OWN <= d.nPml - 2 || wk.x > d.x1 + 2) return;
+    k.lown = (lane >= 1) && (lane <= 30) && colok;
+    k.c1z = d.c1z; k.c2z = d.c2z; k.c1x = d.c1x; k.c2x = d.c2x; k.dt = d.dt;
+    k.ring = EDGE && tile_touches_ring_ext(d, k.zc0 - 2, k.zc1 + 1, wk.x - 4, wk.x + SW_OWN + 3);
+    k.ring_s = smem_warp + lane * 16;
+
+    RecWin w;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 6; j++) { w.szz[j] = w.sxz[j] = w.sxx[j] = w.vz[j] = w.vx[j] = zero; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) { w.ga_prev[c] = 0.f; w.sh_prev[c] = 0.f; }
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), d.nzA - 1) * d.ldx; };
+    const int r0 = k.zc0 - 2;
+    // windows before the first iteration: szz rows r0-1 .. r0+1 (slots 1..3), sxz rows r0-2 .. r0 (slots 0..2)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        w.szz[j + 1] = ldq(k.g + F_SZZ * fsz + rowoff(r0 - 1 + j));
+        w.sxz[j] = ldq(k.g + F_SXZ * fsz + rowoff(r0 - 2 + j));
+    }
+#pragma unroll
+    for (int j = 0; j < RC_NST - 1; j++) stream_rec_issue(k, r0 + j, j);
+    const int niter = (k.zc1 - k.zc0) + 4;
+    if (!EDGE) {
+#pragma unroll 1
+        for (int kk = 0; kk < niter; kk += 6) {
+            const int r = r0 + kk;
+            stream_rec_row<EDGE, 0>(k, w, r, 0 % RC_NST);     stream_rec_row<EDGE, 1>(k, w, r + 1, 1 % RC_NST); stream_rec_row<EDGE, 2>(k, w, r + 2, 2 % RC_NST);
+            stream_rec_row<EDGE, 3>(k, w, r + 3, 3 % RC_NST); stream_rec_row<EDGE, 4>(k, w, r + 4, 4 % RC_NST); stream_rec_row<EDGE, 5>(k, w, r + 5, 5 % RC_NST);
+        }
+    } else {
+        // edge: one row per trip and explicit register moves (keeps the long body inside the instruction cache)
+        int stage = 0;
+#pragma unroll 1
+        for (int kk = 0; kk < niter; kk++) {
+            stream_rec_row<EDGE, 0>(k, w, r0 + kk, stage);
+            stage = stage == RC_NST - 1 ? 0 : stage + 1;
+            // row r+j lives in slot 2+j (old stresses), row r-j in slot (6-j)%6 (new velocities): shift everything one row
+            w.szz[0] = w.szz[1]; w.szz[1] = w.szz[2]; w.szz[2] = w.szz[3]; w.szz[3] = w.szz[4];
+            w.sxz[0] = w.sxz[1]; w.sxz[1] = w.sxz[2]; w.sxz[2] = w.sxz[3];
+            w.sxx[0] = w.sxx[1]; w.sxx[1] = w.sxx[2];
+            w.vz[2] = w.vz[3]; w.vz[3] = w.vz[4]; w.vz[4] = w.vz[5]; w.vz[5] = w.vz[0];
+            w.vx[3] = w.vx[4]; w.vx[4] = w.vx[5]; w.vx[5] = w.vx[0];
+        }
+    }
+    cp_wait<0>();
+}
+
+// grid: x = ceil(nWork / SW_WPB), y = slot ; dynamic shared memory RC_SMEM
+__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_recon(const KArgs a, const StreamArgs sa)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int s = blockIdx.y;
+    const int wg = (int)blockIdx.x * SW_WPB + ((int)threadIdx.x >> 5);
+    if (wg >= sa.nWork) return;
+    const int4 wk = __ldg(sa.work + wg);
+    const int lane = threadIdx.x & 31;
+    const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * RC_WARP_BYTES;
+    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_rec_body<false>(a, sa, s, wk, lane, sw);
+    else stream_rec_body<true>(a, sa, s, wk, lane, sw);
 }
 
 }  // namespace sepfwi

@@ -331,6 +331,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         CU(cudaFuncSetAttribute(k_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         CU(cudaFuncSetAttribute(k_fused_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
         CU(cudaFuncSetAttribute(k_fused_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
+        CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
     }
     size_t of = 0;
     auto takef = [&](size_t n) { size_t o = of; of += n; return o; };
@@ -614,11 +615,12 @@ static int stream_plan(sepfwi_handle *h, int nb, StreamArgs &sa)
     memset(&sa, 0, sizeof(sa));
     const int nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
     // interior rows [zi0, zi1) / strips: the adjoint sweep keeps CPML memory on strips nPml + 2 wide (el_stress_adj.cu:67-72),
-    // and a warp recomputes a 2-cell halo, so the branch-free variant needs a margin of nPml + 4
-    const int zi0 = d.nPml + 4, zi1 = d.nzA - d.nPml - 4;
+    // a warp recomputes a 2-cell halo, and the reverse sweep restores a ring that reaches 3 cells into the interior:
+    // the branch-free variants need a margin of nPml + 5
+    const int zi0 = d.nPml + 5, zi1 = d.nzA - d.nPml - 5;
     const double conc = (double)h->nSM * 2 * SW_WPB;
     const double edge_cost = 1.8;
-    auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 2 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 3; };
+    auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 3 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 4; };
     int nInnerStrips = 0;
     for (int sx = 0; sx < nStrips; sx++) nInnerStrips += strip_inner(sx) ? 1 : 0;
     int best = 8;
@@ -785,6 +787,10 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
             const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
             FusedBwdArgs fa;
             fa.it = it; fa.q = q; fa.pa = pa;
+            if (h->stream && !getenv("SEPFWI_TILE_RECON")) {
+                sa.it = it; sa.q = q; sa.pa = pa;
+                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (k_stream_recon<<<dim3((sa.nWork + SW_WPB - 1) / SW_WPB, nb), SW_NT, RC_SMEM, st>>>(a, sa)));
+            } else
             LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F4_NT, R_SMEM, st>>>(a, fa)));
             if (h->stream) {
                 sa.it = it; sa.q = q; sa.pa = pa;
