@@ -814,27 +814,31 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, co
 // shared-memory ring with cp.async (each lane copies and later reads only its own 16 bytes, so a cp.async.wait_group
 // is the only synchronisation) -- the registers hold just the stencil windows.
 constexpr int RC_NARR = 18;
-constexpr int RC_NST = 3;                                   // ring stages: operands are requested RC_NST-1 rows ahead
+#ifndef RC_NST_
+#define RC_NST_ 2
+#endif
+#ifndef RC_MINB
+#define RC_MINB 2
+#endif
+constexpr int RC_NST = RC_NST_;                             // ring stages: operands are requested RC_NST-1 rows ahead
 constexpr int RC_WARP_BYTES = RC_NST * RC_NARR * 512;       // 27 KB per warp
 constexpr size_t RC_SMEM = (size_t)SW_WPB * RC_WARP_BYTES;  // 108 KB per CTA, 2 CTAs per SM
 enum { RA_SZZ = 0, RA_SXZ, RA_SXX, RA_OVZ, RA_OVX, RA_AVZ, RA_AVX, RA_BA, RA_BB, RA_GR,      // rows r+2, r+1, r, then row r
        RA_ASZZ, RA_ASXZ, RA_ASXX, RA_LAM, RA_MU, RA_MUA, RA_GL, RA_GM };                        // row r-2
 
+#ifndef RC_CP_OP
+#define RC_CP_OP "cp.async.ca.shared.global"
+#endif
 __device__ __forceinline__ void cp16(unsigned saddr, const float *g)
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g)); }
+{ asm volatile(RC_CP_OP " [%0], [%1], 16;" ::"r"(saddr), "l"(g)); }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds4(unsigned saddr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-    return v;
-}
 
 struct RecCtx {
     const float *g, *adj, *m, *ringb, *amp;
     float *o, *grad;
     unsigned ring_s;          // shared-memory address of this lane's 16 bytes in stage 0, array 0
+    const float4 *ring_p;     // the same location as a pointer (plain loads: the compiler schedules them; cp_wait's memory clobber orders them)
     size_t fsz, rfs;
     int ld, nzA, nx, nPml, z1, x1, zc0, zc1, zs, xs, xq0;
     bool lown, ring;
@@ -875,10 +879,10 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
     constexpr int u = U;
     stream_rec_issue(k, r + (RC_NST - 1), stage == 0 ? RC_NST - 1 : stage - 1);
     cp_wait<RC_NST - 1>();
-    const unsigned sb = k.ring_s + (unsigned)stage * (RC_NARR * 512);
-    w.szz[(u + 4) % 6] = lds4(sb + RA_SZZ * 512);       // row r+2
-    w.sxz[(u + 3) % 6] = lds4(sb + RA_SXZ * 512);       // row r+1
-    w.sxx[(u + 2) % 6] = lds4(sb + RA_SXX * 512);       // row r
+    const float4 *sb = k.ring_p + stage * (RC_NARR * 32);
+    w.szz[(u + 4) % 6] = sb[RA_SZZ * 32];       // row r+2
+    w.sxz[(u + 3) % 6] = sb[RA_SXZ * 32];       // row r+1
+    w.sxx[(u + 2) % 6] = sb[RA_SXX * 32];       // row r
     // ---- stage 1: velocities of time `it` at row r ; density imaging
     {
         const float4 p0 = w.szz[(u + 1) % 6], p1 = w.szz[(u + 2) % 6], p2 = w.szz[(u + 3) % 6], p3 = w.szz[(u + 4) % 6];
@@ -887,8 +891,8 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
         const float wxz[7] = XWIN_B(q2), wxx[7] = XWIN_F(xc);
         const float zzm1[4] = Q4(p0), zzc[4] = Q4(p1), zzp1[4] = Q4(p2), zzp2[4] = Q4(p3);
         const float xzm2[4] = Q4(q0), xzm1[4] = Q4(q1), xzc[4] = Q4(q2), xzp1[4] = Q4(q3);
-        const float4 ovz4 = lds4(sb + RA_OVZ * 512), ovx4 = lds4(sb + RA_OVX * 512), avz4 = lds4(sb + RA_AVZ * 512), avx4 = lds4(sb + RA_AVX * 512);
-        const float4 ba4 = lds4(sb + RA_BA * 512), bb4 = lds4(sb + RA_BB * 512);
+        const float4 ovz4 = sb[RA_OVZ * 32], ovx4 = sb[RA_OVX * 32], avz4 = sb[RA_AVZ * 32], avx4 = sb[RA_AVX * 32];
+        const float4 ba4 = sb[RA_BA * 32], bb4 = sb[RA_BB * 32];
         const float ovz[4] = Q4(ovz4), ovx[4] = Q4(ovx4), avz[4] = Q4(avz4), avx[4] = Q4(avx4), ba[4] = Q4(ba4), bb[4] = Q4(bb4);
         float nvz[4], nvx[4], ga[4], gb[4];
 #pragma unroll
@@ -915,7 +919,7 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
         const bool rreg = !EDGE || (r >= k.nPml - 2 && r <= k.z1 + 2 && k.xq0 + 3 >= k.nPml - 2 && k.xq0 <= k.x1 + 2);
         if (k.lown && rown && rreg) {
             const size_t ro = (size_t)r * ld;
-            const float4 g4 = lds4(sb + RA_GR * 512);
+            const float4 g4 = sb[RA_GR * 32];
             float gr[4] = Q4(g4);
             const float gbW[5] = {gbl, gb[0], gb[1], gb[2], gb[3]};
             const bool zle = !EDGE || (r <= k.z1);
@@ -941,8 +945,8 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
         const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
         const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
         const float ozz[4] = Q4(w.szz[u % 6]), oxz[4] = Q4(w.sxz[u % 6]), oxx[4] = Q4(w.sxx[u % 6]);     // old stresses of row r-2: slot u
-        const float4 za4 = lds4(sb + RA_ASZZ * 512), sa4 = lds4(sb + RA_ASXZ * 512), xa4 = lds4(sb + RA_ASXX * 512);
-        const float4 lam4 = lds4(sb + RA_LAM * 512), mu4 = lds4(sb + RA_MU * 512), mua4 = lds4(sb + RA_MUA * 512);
+        const float4 za4 = sb[RA_ASZZ * 32], sa4 = sb[RA_ASXZ * 32], xa4 = sb[RA_ASXX * 32];
+        const float4 lam4 = sb[RA_LAM * 32], mu4 = sb[RA_MU * 32], mua4 = sb[RA_MUA * 32];
         const float za[4] = Q4(za4), sa[4] = Q4(sa4), xa[4] = Q4(xa4), lam[4] = Q4(lam4), mu[4] = Q4(mu4), mua[4] = Q4(mua4);
         float D1[4], D2[4], D3[4], sh[4];
 #pragma unroll
@@ -958,7 +962,7 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
         const bool qreg = !EDGE || (q >= k.nPml - 2 && q <= k.z1 + 2 && k.xq0 + 3 >= k.nPml - 2 && k.xq0 <= k.x1 + 2);
         if (k.lown && qown && qreg) {
             const size_t ro = (size_t)q * ld;
-            const float4 g0 = lds4(sb + RA_GL * 512), g1 = lds4(sb + RA_GM * 512);
+            const float4 g0 = sb[RA_GL * 32], g1 = sb[RA_GM * 32];
             float gl[4] = Q4(g0), gm[4] = Q4(g1);
             const float shW[5] = {shl, sh[0], sh[1], sh[2], sh[3]}, shUW[5] = {shul, w.sh_prev[0], w.sh_prev[1], w.sh_prev[2], w.sh_prev[3]};
             float nzz[4], nxz[4], nxx[4];
@@ -999,7 +1003,7 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
 }
 
 template <bool EDGE>
-__device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, const unsigned smem_warp)
+__device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, const unsigned smem_warp, const float4 *ring_ptr)
 {
     const Dims &d = a.d;
     RecCtx k;
@@ -1027,6 +1031,7 @@ __device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs
     k.c1z = d.c1z; k.c2z = d.c2z; k.c1x = d.c1x; k.c2x = d.c2x; k.dt = d.dt;
     k.ring = EDGE && tile_touches_ring_ext(d, k.zc0 - 2, k.zc1 + 1, wk.x - 4, wk.x + SW_OWN + 3);
     k.ring_s = smem_warp + lane * 16;
+    k.ring_p = ring_ptr + lane;
 
     RecWin w;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1071,7 +1076,7 @@ __device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs
 }
 
 // grid: x = ceil(nWork / SW_WPB), y = slot ; dynamic shared memory RC_SMEM
-__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_recon(const KArgs a, const StreamArgs sa)
+__global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, const StreamArgs sa)
 {
     extern __shared__ __align__(16) float smem[];
     const int s = blockIdx.y;
@@ -1080,8 +1085,9 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_recon(const KArgs a, 
     const int4 wk = __ldg(sa.work + wg);
     const int lane = threadIdx.x & 31;
     const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * RC_WARP_BYTES;
-    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_rec_body<false>(a, sa, s, wk, lane, sw);
-    else stream_rec_body<true>(a, sa, s, wk, lane, sw);
+    const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (RC_WARP_BYTES / 16);
+    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);
+    else stream_rec_body<true>(a, sa, s, wk, lane, sw, sp);
 }
 
 }  // namespace sepfwi
