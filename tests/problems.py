@@ -115,6 +115,23 @@ def small_adj():
     return small(adjacent=True)
 
 
+def medium(fiber=0, nx=291):
+    """150 x 291 interior (padded width 307: odd, three 120-column strips), nPml 8, 2 shots, 170 ADJACENT
+    receivers crossing the strip seams at x = 120 and 240, 180 steps.  Big enough that the streaming kernels run
+    their branch-free interior variant next to the CPML variant; too big for the oracle in the CPU suite, so it
+    is checked on the GPU against the baseline kernels (which the small problems pin to the oracle)."""
+    rng = np.random.default_rng(11)
+    nz = 150
+    vt = layered_vp(nz, nx, 1800.0, 3400.0, 5, rng, nlens=14, lens_amp=0.1, sigma=(4, 16))
+    vs = smooth(vt, 6)
+    if fiber == 0:
+        z_rec, x_rec = np.full(170, 60), np.arange(70, 240)
+    else:
+        z_rec, x_rec = np.arange(5, 145), np.full(140, 113)       # padded column 121: first owned quad of strip 1
+    return Problem("medium" + ("_ezz" if fiber else ""), nz, nx, 8, 10.0, 10.0, 1.0e-3, 180, 16.0, vt, vs,
+                   [2, 70], [30, 231], z_rec, x_rec, fiber)
+
+
 def reference_test(nSteps=1501, nshots=19):
     """The reference's own test problem (notebooks/Main-001-...py:28-72):
     101 x 201, dx=dz=20, dt=2 ms, nPml 32, 19 shots at z=1, 181 receivers at z=95,

@@ -68,6 +68,54 @@ def test_fused_kernels_match_baseline_kernels(mk, batch):
         assert rel_l2(res[0][1][k], res[1][1][k]) < 5e-5, k
 
 
+def _run_both(prob, kern, batch=2, weights=None):
+    O, Propagator, ShotSpec = _mods()
+    with make_prop(Propagator, prob, max_batch=batch, with_adjoint=True, kernels=kern) as P:
+        P.set_model(*prob.true)
+        shots = cuda_shots(prob, ShotSpec)
+        if weights is not None:
+            for sh in shots:
+                sh.weights = weights
+        fwd = P.forward(shots)
+        P.set_model(*prob.start)
+        g = P.gradient(shots, [f["ett"] for f in fwd])
+    return fwd, g
+
+
+def _assert_same(a, b, nshots, tol_tr=1e-5, tol_g=5e-5):
+    for sid in range(nshots):
+        for c in ("pr", "vx", "vz", "ett"):
+            assert rel_l2(a[0][sid][c], b[0][sid][c]) < tol_tr, (sid, c)
+    assert abs(a[1]["misfit"] - b[1]["misfit"]) <= 1e-5 * abs(b[1]["misfit"])
+    for k in ("glam", "gmu", "grho"):
+        assert rel_l2(a[1][k], b[1][k]) < tol_g, k
+    assert rel_l2(np.stack(a[1]["gstf"]), np.stack(b[1]["gstf"])) < tol_g
+
+
+@pytest.mark.parametrize("fiber,lz", [(0, None), (1, None), (0, "8"), (0, "26"), (1, "50")])
+def test_streaming_kernels_interior_and_seams(fiber, lz, monkeypatch):
+    """Medium grid: three strips (odd padded width), interior + CPML warps, adjacent receivers across the strip seams
+    (injection targets that sit in two strips), several chunk heights.  Streaming kernels vs baseline kernels."""
+    if lz is not None:
+        monkeypatch.setenv("SEPFWI_LZ", lz)
+    prob = problems.medium(fiber=fiber)
+    _assert_same(_run_both(prob, 0), _run_both(prob, 1), prob.nshots)
+
+
+def test_streaming_kernels_general_fiber_weights():
+    """Per-channel (exx, ezz, exz) sensitivities through the streaming record / injection paths."""
+    prob = problems.medium(nx=250)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(-1.0, 1.0, (len(prob.x_rec), 3)).astype(np.float32)
+    _assert_same(_run_both(prob, 0, weights=w), _run_both(prob, 1, weights=w), prob.nshots)
+
+
+def test_tile_kernels_still_match_baseline():
+    """kernels = 2 (shared-memory tile kernels, the previous default) stays a valid cross-check path."""
+    prob = problems.small()
+    _assert_same(_run_both(prob, 2, batch=3), _run_both(prob, 1, batch=3), prob.nshots)
+
+
 def test_cpml_profiles_match_oracle():
     O, Propagator, _ = _mods()
     prob = problems.small()
