@@ -281,7 +281,7 @@ def main():
         ms, n = prof.get(name, (0.0, 0))
         return ms / n if n else 0.0
 
-    fwd_kernels = [k for k in ("fused_fwd", "stress_fwd", "velocity_fwd") if k in prof]
+    fwd_kernels = [k for k in ("stream_fwd", "fused_fwd", "stress_fwd", "velocity_fwd") if k in prof]
     t_fwd_step = sum(avg(k) for k in fwd_kernels) * 1e-3
     roof = None
     if t_fwd_step > 0:
@@ -293,7 +293,7 @@ def main():
                         % ("+".join(fwd_kernels), 13 * w["live"] * 4 / 1e6, "fits in" if 13 * w["live"] * 4 < 100e6 else "exceeds"),
                 "per_kernel_us": {k: 1e3 * avg(k) for k in prof}}
         if is_grad:
-            bk = [k for k in ("fused_recon", "fused_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj", "inject") if k in prof]
+            bk = [k for k in ("stream_recon", "stream_adj", "fused_recon", "fused_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj", "inject") if k in prof]
             t_b = sum(avg(k) for k in bk) * 1e-3
             if t_b > 0:
                 achb = (B_ADJ * w["live"] + B_REC * w["interior"]) / t_b / 1e9
@@ -414,8 +414,8 @@ def extra_large(args, Propagator, ShotSpec, torch, dev, local, peak):
         prof = P.profile()
         f_ms, b_ms = P.last_timing()
         us = {k: 1e3 * ms / n for k, (ms, n) in prof.items()}
-        fk = [k for k in ("fused_fwd", "stress_fwd", "velocity_fwd") if k in us]
-        bk = [k for k in ("fused_recon", "fused_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in us]
+        fk = [k for k in ("stream_fwd", "fused_fwd", "stress_fwd", "velocity_fwd") if k in us]
+        bk = [k for k in ("stream_recon", "stream_adj", "fused_recon", "fused_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in us]
         tf, tb = sum(us[k] for k in fk) * 1e-6, sum(us[k] for k in bk) * 1e-6
         af = B_FWD * w["live"] / tf / 1e9
         ab = (B_ADJ * w["live"] + B_REC * w["interior"]) / tb / 1e9

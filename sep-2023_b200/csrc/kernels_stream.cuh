@@ -45,6 +45,10 @@ struct StreamArgs {
 };
 
 #define Q4(v) {v.x, v.y, v.z, v.w}
+// Programmatic dependent launch: every kernel of a time loop lets its successor start launching right away and
+// waits for its predecessor's results only after its own set-up -- removes the ~2-4 us launch gap per time step.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // streaming 128-bit load of data that is read-only for the whole launch (L1 allocation kept: the 8-column overlap
 // of adjacent strips is served by L1 when the neighbouring warp sits in the same CTA)
 __device__ __forceinline__ float4 ldq(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
@@ -405,11 +409,13 @@ __device__ __forceinline__ void stream_fwd_edge(const KArgs &a, const StreamArgs
 // grid: x = nAux + ceil(nWork / SW_WPB), y = slot
 __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_fwd(const KArgs a, const StreamArgs sa)
 {
+    pdl_launch_dependents();
     const int s = blockIdx.y;
-    if ((int)blockIdx.x < sa.nAux) { stream_fwd_aux(a, sa, s); return; }
+    if ((int)blockIdx.x < sa.nAux) { pdl_wait(); stream_fwd_aux(a, sa, s); return; }
     const int wg = ((int)blockIdx.x - sa.nAux) * SW_WPB + ((int)threadIdx.x >> 5);
     if (wg >= sa.nWork) return;      // whole warp leaves (the in-place CPML memory must not be updated twice)
     const int4 wk = __ldg(sa.work + wg);
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_fwd_body<false>(a, sa, s, wk, lane);
     else stream_fwd_edge(a, sa, s, wk, lane);
@@ -786,9 +792,11 @@ __device__ __forceinline__ void stream_adj_edge(const KArgs &a, const StreamArgs
 __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, const StreamArgs sa)
 {
     __shared__ __align__(16) float stage[SW_WPB][256];
+    pdl_launch_dependents();
     const int s = blockIdx.y;
     const Dims &d = a.d;
     if (blockIdx.x == 0) {
+        pdl_wait();
         if (threadIdx.x == 0) {      // source_grad, utilities.cu:719-730, from the adjoint state after step it+1
             const float *src = slot_state(a, s) + (size_t)(sa.pa ? S_ADJ1 : S_ADJ) * d.fsz;
             const size_t i = (size_t)a.t.zs[s] * d.ldx + a.t.xs[s];
@@ -800,6 +808,7 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, co
     if (wg >= sa.nWork) return;
     const int4 wk = __ldg(sa.work + wg);
     const int lane = threadIdx.x & 31;
+    pdl_wait();
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_adj_body<false>(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
     else stream_adj_edge(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
 }
@@ -1079,11 +1088,13 @@ __device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs
 __global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, const StreamArgs sa)
 {
     extern __shared__ __align__(16) float smem[];
+    pdl_launch_dependents();
     const int s = blockIdx.y;
     const int wg = (int)blockIdx.x * SW_WPB + ((int)threadIdx.x >> 5);
     if (wg >= sa.nWork) return;
     const int4 wk = __ldg(sa.work + wg);
     const int lane = threadIdx.x & 31;
+    pdl_wait();
     const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * RC_WARP_BYTES;
     const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (RC_WARP_BYTES / 16);
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);

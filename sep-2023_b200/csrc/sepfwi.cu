@@ -67,6 +67,7 @@ struct sepfwi_handle {
     bool fused = false;    // tile kernels (kernels = 2); their backward half also serves kernels = 0 until the streaming one lands
     bool stream = false;   // register-streaming kernels (kernels = 0)
     int nSM = 148;
+    bool pdl = true;       // programmatic dependent launch inside the time loops (SEPFWI_PDL=0 disables)
     int4 *work = nullptr;  // work list of the streaming kernels (device)
     size_t work_cap = 0;
     size_t o_amp, o_rxz, o_w, o_injCoef;
@@ -90,6 +91,20 @@ struct sepfwi_handle {
 
 static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
                                               "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_recon", "fused_adj", "stream_fwd", "stream_recon", "stream_adj"};
+
+// Launch with programmatic stream serialization (the kernels call griddepcontrol.launch_dependents / .wait themselves).
+template <typename... KA, typename... A>
+static void launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, A... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 // launch `stmt` and, in profile mode, bracket it with an event pair
 #define LAUNCH(h, KND, prof_on, st, stmt)                                     \
@@ -321,6 +336,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     h->o_sInjPtr = takei((size_t)B * h->nStrips * (d.nzA + 1)); h->o_sInj = takei((size_t)B * 2 * maxInj);
     h->n_int = oi;
     h->stream = !h->sponge && pp->kernels == 0;
+    if (const char *e = getenv("SEPFWI_PDL")) h->pdl = atoi(e) != 0;
     h->fused = !h->sponge && (pp->kernels == 0 || pp->kernels == 2);
     {
         cudaDeviceProp prop;
@@ -683,12 +699,12 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
         if (rc) return rc;
         sa.fiber = h->p.fiber; sa.save_ring = save_ring ? 1 : 0; sa.nrecMax = mrec;
         const int items = (mrec > 0 ? mrec : 0) + (save_ring ? d.ringLen : 0);
-        sa.nAux = items > 0 ? std::min(64, (items + SW_NT * 8 - 1) / (SW_NT * 8)) : 0;
+        sa.nAux = items > 0 ? std::min(h->nSM, (items + 2 * SW_NT - 1) / (2 * SW_NT)) : 0;      // two items per thread while that stays below one CTA per SM
         dim3 sgrd(sa.nAux + (sa.nWork + SW_WPB - 1) / SW_WPB, nb);
         for (int it = 0; it <= d.nSteps - 2; it++) {
             const bool pr = it < h->prof_steps;
             sa.it = it; sa.mask = (it >= 1 && mrec > 0) ? mask : 0;
-            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (k_stream_fwd<<<sgrd, SW_NT, 0, st>>>(a, sa)));
+            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), 0, st, h->pdl, a, sa)));
         }
         const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state
         if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, false, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, d.nSteps - 1, mask, h->p.fiber, par)));
@@ -789,12 +805,12 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
             fa.it = it; fa.q = q; fa.pa = pa;
             if (h->stream && !getenv("SEPFWI_TILE_RECON")) {
                 sa.it = it; sa.q = q; sa.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (k_stream_recon<<<dim3((sa.nWork + SW_WPB - 1) / SW_WPB, nb), SW_NT, RC_SMEM, st>>>(a, sa)));
+                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (launch_pdl(k_stream_recon, dim3((sa.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM, st, h->pdl, a, sa)));
             } else
             LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F4_NT, R_SMEM, st>>>(a, fa)));
             if (h->stream) {
                 sa.it = it; sa.q = q; sa.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (k_stream_adj<<<sagrd, SW_NT, 0, st>>>(a, sa)));
+                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (launch_pdl(k_stream_adj, sagrd, dim3(SW_NT), 0, st, h->pdl, a, sa)));
             } else
             LAUNCH(h, SEPFWI_K_FUSED_ADJ, pr, st, (k_fused_adj<<<agrd, F4_NT, A_SMEM, st>>>(a, fa)));
             q ^= 1; pa ^= 1;
