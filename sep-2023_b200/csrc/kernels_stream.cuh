@@ -120,51 +120,85 @@ __device__ __forceinline__ void stream_fwd_aux(const KArgs &a, const StreamArgs 
     }
 }
 
+#ifndef RC_CP_OP
+#define RC_CP_OP "cp.async.ca.shared.global"
+#endif
+__device__ __forceinline__ void cp16(unsigned saddr, const float *g)
+{ asm volatile(RC_CP_OP " [%0], [%1], 16;" ::"r"(saddr), "l"(g)); }
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // forward step of one (strip, chunk)
+//
+// Operand ring: the ten (interior) or eighteen (edge: + eight CPML memory variables) row quads an iteration needs are
+// requested FR_NST-1 rows ahead with cp.async into a per-warp shared-memory ring; each lane copies and later reads only
+// its own 16 bytes, so cp.async.wait_group is the only synchronisation and the registers hold just the stencil windows.
+constexpr int FR_NARR_I = 10, FR_NST_I = 3;                 // interior: 3 stages x 10 arrays x 512 B = 15 KB per warp
+constexpr int FR_NARR_E = 18, FR_NST_E = 2;                 // edge:     2 stages x 18 arrays x 512 B = 18 KB per warp
+constexpr int FR_WARP_BYTES = FR_NARR_E * FR_NST_E * 512;
+constexpr size_t FR_SMEM = (size_t)SW_WPB * FR_WARP_BYTES;  // 72 KB per CTA, 2 CTAs per SM
+enum { FA_VZ = 0, FA_VX, FA_OZZ, FA_OXZ, FA_OXX, FA_LAM, FA_MU, FA_MUA, FA_BYA, FA_BYB,       // rows r+2 (v), r, r-2 (buoyancies)
+       FA_PVZZ, FA_PVXZ, FA_PVXX, FA_PVZX, FA_PSZZ, FA_PSXZZ, FA_PSXZX, FA_PSXX };              // CPML memory: rows r (stress side), r-2 (velocity side)
+
 struct FwdCtx {          // per-warp constants of the march
     const float *g, *m, *pv_src, *cxs, *cxv, *cz, *amp;
     float *o, *pv_dst, *ps;
+    const float4 *ring_p;    // this lane's 16 bytes of stage 0, array 0
+    unsigned ring_s;         // the same as a shared-memory address
     size_t fsz;
     int ld, nzA, nPml, zc0, zc1, zs, xs, xq0;
     unsigned amask;
     bool lown, xps, xpv;
     float c1z, c2z, c1x, c2x, dt;
 };
-struct FwdWin {          // register windows and the double-buffered row operands
+struct FwdWin {          // register windows: old velocities rows r-2 .. r+2, new stresses rows r-4 .. r
     float4 vz[6], vx[6], zz[6], xz[6], xx[6];
-    float4 ozz[2], oxz[2], oxx[2], lam[2], mu[2], mua[2], bya[2], byb[2];
 };
 
-// one row: prefetch row r+1's operands, stress at row r, velocity at row r-2.  U = r's phase in the 6-slot rotation.
-template <bool EDGE, int U>
-__device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const int r)
+template <bool EDGE>
+__device__ __forceinline__ bool fwd_zp(const FwdCtx &k, int row)      // row inside the z CPML strips and active
+{ return EDGE && row >= 2 && row <= k.nzA - 3 && ((row < k.nPml) || (row > k.nzA - k.nPml - 1)); }
+
+// request the operands of the iteration whose stress row is r
+template <bool EDGE>
+__device__ __forceinline__ void stream_fwd_issue(const FwdCtx &k, const int r, const int stage)
 {
+    constexpr int NARR = EDGE ? FR_NARR_E : FR_NARR_I;
+    const int ld = k.ld, nzA = k.nzA;
+    const size_t fsz = k.fsz;
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };   // clamped rows feed inactive / unowned cells only
+    const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
+    const unsigned sb = k.ring_s + (unsigned)stage * (NARR * 512);
+    cp16(sb + FA_VZ * 512, k.g + F_VZ * fsz + r2); cp16(sb + FA_VX * 512, k.g + F_VX * fsz + r2);
+    cp16(sb + FA_OZZ * 512, k.g + F_SZZ * fsz + r0); cp16(sb + FA_OXZ * 512, k.g + F_SXZ * fsz + r0); cp16(sb + FA_OXX * 512, k.g + F_SXX * fsz + r0);
+    cp16(sb + FA_LAM * 512, k.m + M_LAM * fsz + r0); cp16(sb + FA_MU * 512, k.m + M_MU * fsz + r0); cp16(sb + FA_MUA * 512, k.m + M_MUAVE * fsz + r0);
+    cp16(sb + FA_BYA * 512, k.m + M_BYCA * fsz + rq); cp16(sb + FA_BYB * 512, k.m + M_BYCB * fsz + rq);
+    if (EDGE) {
+        const int q = r - 2;
+        const bool ract = (r >= 2 && r <= nzA - 3), qact = (q >= 2 && q <= nzA - 3) && (q >= k.zc0) && (q < k.zc1);
+        if (fwd_zp<EDGE>(k, r)) { cp16(sb + FA_PVZZ * 512, k.pv_src + (size_t)P_VZ_Z * fsz + r0); cp16(sb + FA_PVXZ * 512, k.pv_src + (size_t)P_VX_Z * fsz + r0); }
+        if (ract && k.xps) { cp16(sb + FA_PVXX * 512, k.pv_src + (size_t)P_VX_X * fsz + r0); cp16(sb + FA_PVZX * 512, k.pv_src + (size_t)P_VZ_X * fsz + r0); }
+        if (qact && fwd_zp<EDGE>(k, q)) { cp16(sb + FA_PSZZ * 512, k.ps + (size_t)P_SZZ_Z * fsz + rq); cp16(sb + FA_PSXZZ * 512, k.ps + (size_t)P_SXZ_Z * fsz + rq); }
+        if (qact && k.xpv && k.lown) { cp16(sb + FA_PSXZX * 512, k.ps + (size_t)P_SXZ_X * fsz + rq); cp16(sb + FA_PSXX * 512, k.ps + (size_t)P_SXX_X * fsz + rq); }
+    }
+    cp_commit();
+}
+
+// one row: request row r + (NST-1), then stress at row r and velocity at row r-2.  U = r's phase in the 6-slot rotation.
+template <bool EDGE, int U>
+__device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const int r, const int stage)
+{
+    constexpr int NARR = EDGE ? FR_NARR_E : FR_NARR_I;
+    constexpr int NST = EDGE ? FR_NST_E : FR_NST_I;
     const int ld = k.ld, nzA = k.nzA;
     const size_t fsz = k.fsz;
     const float c1z = k.c1z, c2z = k.c2z, c1x = k.c1x, c2x = k.c2x, dt = k.dt;
     constexpr int u = U;
-    constexpr int cb = u & 1, nb = cb ^ 1;
-    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };   // clamped rows feed inactive / unowned cells only
-    if (!EDGE) {   // ---- prefetch the rows of the next iteration (register double buffering)
-        const size_t r3 = rowoff(r + 3), r1 = rowoff(r + 1), rq = rowoff(r - 1);
-        w.vz[(u + 5) % 6] = ldq(k.g + F_VZ * fsz + r3); w.vx[(u + 5) % 6] = ldq(k.g + F_VX * fsz + r3);
-        w.ozz[nb] = ldq(k.g + F_SZZ * fsz + r1); w.oxz[nb] = ldq(k.g + F_SXZ * fsz + r1); w.oxx[nb] = ldq(k.g + F_SXX * fsz + r1);
-        w.lam[nb] = ldq(k.m + M_LAM * fsz + r1); w.mu[nb] = ldq(k.m + M_MU * fsz + r1); w.mua[nb] = ldq(k.m + M_MUAVE * fsz + r1);
-        w.bya[nb] = ldq(k.m + M_BYCA * fsz + rq); w.byb[nb] = ldq(k.m + M_BYCB * fsz + rq);
-    } else {       // ---- edge warps: this row's operands, no look-ahead (the extra CPML state needs the registers; these
-                   //      few warps are latency-bound either way and overlap with the interior warps of the SM)
-        const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
-        w.vz[(u + 4) % 6] = ldq(k.g + F_VZ * fsz + r2); w.vx[(u + 4) % 6] = ldq(k.g + F_VX * fsz + r2);
-        w.ozz[cb] = ldq(k.g + F_SZZ * fsz + r0); w.oxz[cb] = ldq(k.g + F_SXZ * fsz + r0); w.oxx[cb] = ldq(k.g + F_SXX * fsz + r0);
-        w.lam[cb] = ldq(k.m + M_LAM * fsz + r0); w.mu[cb] = ldq(k.m + M_MU * fsz + r0); w.mua[cb] = ldq(k.m + M_MUAVE * fsz + r0);
-        w.bya[cb] = ldq(k.m + M_BYCA * fsz + rq); w.byb[cb] = ldq(k.m + M_BYCB * fsz + rq);
-        const size_t n2 = rowoff(r + 3), n0 = rowoff(r + 1), nq = rowoff(r - 1);
-        pf_l1(k.g + F_VZ * fsz + n2); pf_l1(k.g + F_VX * fsz + n2);
-        pf_l1(k.g + F_SZZ * fsz + n0); pf_l1(k.g + F_SXZ * fsz + n0); pf_l1(k.g + F_SXX * fsz + n0);
-        pf_l1(k.m + M_LAM * fsz + n0); pf_l1(k.m + M_MU * fsz + n0); pf_l1(k.m + M_MUAVE * fsz + n0);
-        pf_l1(k.m + M_BYCA * fsz + nq); pf_l1(k.m + M_BYCB * fsz + nq);
-    }
+    stream_fwd_issue<EDGE>(k, r + (NST - 1), stage == 0 ? NST - 1 : stage - 1);
+    cp_wait<NST - 1>();
+    const float4 *sb = k.ring_p + stage * (NARR * 32);
+    w.vz[(u + 4) % 6] = sb[FA_VZ * 32]; w.vx[(u + 4) % 6] = sb[FA_VX * 32];       // row r+2
     // ---- stress at row r from v rows r-2 .. r+2 (slots u .. u+4)
     {
         const float4 a0 = w.vz[u % 6], a1 = w.vz[(u + 1) % 6], a2 = w.vz[(u + 2) % 6], a3 = w.vz[(u + 3) % 6];
@@ -172,11 +206,13 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
         const float vxc[7] = XWIN_B(b1), vzc[7] = XWIN_F(a2);
         const float vzm2[4] = Q4(a0), vzm1[4] = Q4(a1), vzq[4] = Q4(a2), vzp1[4] = Q4(a3);
         const float vxm1[4] = Q4(b0), vxq[4] = Q4(b1), vxp1[4] = Q4(b2), vxp2[4] = Q4(b3);
-        const float l[4] = Q4(w.lam[cb]), mm[4] = Q4(w.mu[cb]), ma[4] = Q4(w.mua[cb]);
-        const float pzz[4] = Q4(w.ozz[cb]), pxz[4] = Q4(w.oxz[cb]), pxx[4] = Q4(w.oxx[cb]);
+        const float4 lam4 = sb[FA_LAM * 32], mu4 = sb[FA_MU * 32], mua4 = sb[FA_MUA * 32];
+        const float4 ozz4 = sb[FA_OZZ * 32], oxz4 = sb[FA_OXZ * 32], oxx4 = sb[FA_OXX * 32];
+        const float l[4] = Q4(lam4), mm[4] = Q4(mu4), ma[4] = Q4(mua4);
+        const float pzz[4] = Q4(ozz4), pxz[4] = Q4(oxz4), pxx[4] = Q4(oxx4);
         float nzz[4], nxz[4], nxx[4];
         const bool rowact = !EDGE || (r >= 2 && r <= nzA - 3);
-        const bool zp = EDGE && rowact && ((r < k.nPml) || (r > nzA - k.nPml - 1));
+        const bool zp = fwd_zp<EDGE>(k, r);
         const bool xp = EDGE && rowact && k.xps;
         const bool rown = (r >= k.zc0) && (r < k.zc1);
         const size_t ro = (size_t)r * ld;       // only dereferenced for owned / active rows
@@ -185,7 +221,7 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
         float bx[4], ax[4], rkx[4], bxh[4], axh[4], rkxh[4];
         if (EDGE) {
             if (zp) {
-                const float4 t0 = ldq(k.pv_src + (size_t)P_VZ_Z * fsz + ro), t1 = ldq(k.pv_src + (size_t)P_VX_Z * fsz + ro);
+                const float4 t0 = sb[FA_PVZZ * 32], t1 = sb[FA_PVXZ * 32];
                 pzq[0] = t0.x; pzq[1] = t0.y; pzq[2] = t0.z; pzq[3] = t0.w;
                 pzh[0] = t1.x; pzh[1] = t1.y; pzh[2] = t1.z; pzh[3] = t1.w;
                 const float *cz = k.cz + r;
@@ -193,12 +229,12 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
                 bzh = cz[C_BH * nzA]; azh = cz[C_AH * nzA]; rkzh = cz[C_RKH * nzA];
             }
             if (xp) {
-                const float4 t0 = ldq(k.pv_src + (size_t)P_VX_X * fsz + ro), t1 = ldq(k.pv_src + (size_t)P_VZ_X * fsz + ro);
+                const float4 t0 = sb[FA_PVXX * 32], t1 = sb[FA_PVZX * 32];
                 pxq[0] = t0.x; pxq[1] = t0.y; pxq[2] = t0.z; pxq[3] = t0.w;
                 pxh[0] = t1.x; pxh[1] = t1.y; pxh[2] = t1.z; pxh[3] = t1.w;
                 const float *cx = k.cxs;
-                const float4 q0 = ldq(cx + C_B * ld), q1 = ldq(cx + C_A * ld), q2 = ldq(cx + C_RK * ld);
-                const float4 q3 = ldq(cx + C_BH * ld), q4 = ldq(cx + C_AH * ld), q5 = ldq(cx + C_RKH * ld);
+                const float4 q0 = ldq_c(cx + C_B * ld), q1 = ldq_c(cx + C_A * ld), q2 = ldq_c(cx + C_RK * ld);
+                const float4 q3 = ldq_c(cx + C_BH * ld), q4 = ldq_c(cx + C_AH * ld), q5 = ldq_c(cx + C_RKH * ld);
                 bx[0] = q0.x; bx[1] = q0.y; bx[2] = q0.z; bx[3] = q0.w; ax[0] = q1.x; ax[1] = q1.y; ax[2] = q1.z; ax[3] = q1.w;
                 rkx[0] = q2.x; rkx[1] = q2.y; rkx[2] = q2.z; rkx[3] = q2.w; bxh[0] = q3.x; bxh[1] = q3.y; bxh[2] = q3.z; bxh[3] = q3.w;
                 axh[0] = q4.x; axh[1] = q4.y; axh[2] = q4.z; axh[3] = q4.w; rkxh[0] = q5.x; rkxh[1] = q5.y; rkxh[2] = q5.z; rkxh[3] = q5.w;
@@ -255,11 +291,12 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
         const float zzm1[4] = Q4(p0), zzc[4] = Q4(p1), zzp1[4] = Q4(p2), zzp2[4] = Q4(p3);
         const float xzm2[4] = Q4(q0), xzm1[4] = Q4(q1), xzp1[4] = Q4(q3);
         const float ovz[4] = Q4(w.vz[u % 6]), ovx[4] = Q4(w.vx[u % 6]);      // v row r-2 lives in slot u
-        const float ba[4] = Q4(w.bya[cb]), bb[4] = Q4(w.byb[cb]);
+        const float4 bya4 = sb[FA_BYA * 32], byb4 = sb[FA_BYB * 32];
+        const float ba[4] = Q4(bya4), bb[4] = Q4(byb4);
         float nvz[4], nvx[4];
         const bool qown = (q >= k.zc0) && (q < k.zc1);
         const bool rowact = !EDGE || (q >= 2 && q <= nzA - 3);
-        const bool zp = EDGE && rowact && qown && ((q < k.nPml) || (q > nzA - k.nPml - 1));
+        const bool zp = qown && fwd_zp<EDGE>(k, q);
         const bool xp = EDGE && rowact && qown && k.xpv && k.lown;
         const size_t ro = (size_t)q * ld;
         float pzq[4] = {0.f, 0.f, 0.f, 0.f}, pzh[4] = {0.f, 0.f, 0.f, 0.f}, pxq[4] = {0.f, 0.f, 0.f, 0.f}, pxh[4] = {0.f, 0.f, 0.f, 0.f};
@@ -267,7 +304,7 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
         float bx[4], ax[4], rkx[4], bxh[4], axh[4], rkxh[4];
         if (EDGE) {
             if (zp) {
-                const float4 t0 = ldq_rw(k.ps + (size_t)P_SZZ_Z * fsz + ro), t1 = ldq_rw(k.ps + (size_t)P_SXZ_Z * fsz + ro);
+                const float4 t0 = sb[FA_PSZZ * 32], t1 = sb[FA_PSXZZ * 32];
                 pzh[0] = t0.x; pzh[1] = t0.y; pzh[2] = t0.z; pzh[3] = t0.w;
                 pzq[0] = t1.x; pzq[1] = t1.y; pzq[2] = t1.z; pzq[3] = t1.w;
                 const float *cz = k.cz + q;
@@ -275,12 +312,12 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
                 bzh = cz[C_BH * nzA]; azh = cz[C_AH * nzA]; rkzh = cz[C_RKH * nzA];
             }
             if (xp) {
-                const float4 t0 = ldq_rw(k.ps + (size_t)P_SXZ_X * fsz + ro), t1 = ldq_rw(k.ps + (size_t)P_SXX_X * fsz + ro);
+                const float4 t0 = sb[FA_PSXZX * 32], t1 = sb[FA_PSXX * 32];
                 pxq[0] = t0.x; pxq[1] = t0.y; pxq[2] = t0.z; pxq[3] = t0.w;
                 pxh[0] = t1.x; pxh[1] = t1.y; pxh[2] = t1.z; pxh[3] = t1.w;
                 const float *cx = k.cxv;
-                const float4 e0 = ldq(cx + C_B * ld), e1 = ldq(cx + C_A * ld), e2 = ldq(cx + C_RK * ld);
-                const float4 e3 = ldq(cx + C_BH * ld), e4 = ldq(cx + C_AH * ld), e5 = ldq(cx + C_RKH * ld);
+                const float4 e0 = ldq_c(cx + C_B * ld), e1 = ldq_c(cx + C_A * ld), e2 = ldq_c(cx + C_RK * ld);
+                const float4 e3 = ldq_c(cx + C_BH * ld), e4 = ldq_c(cx + C_AH * ld), e5 = ldq_c(cx + C_RKH * ld);
                 bx[0] = e0.x; bx[1] = e0.y; bx[2] = e0.z; bx[3] = e0.w; ax[0] = e1.x; ax[1] = e1.y; ax[2] = e1.z; ax[3] = e1.w;
                 rkx[0] = e2.x; rkx[1] = e2.y; rkx[2] = e2.z; rkx[3] = e2.w; bxh[0] = e3.x; bxh[1] = e3.y; bxh[2] = e3.z; bxh[3] = e3.w;
                 axh[0] = e4.x; axh[1] = e4.y; axh[2] = e4.z; axh[3] = e4.w; rkxh[0] = e5.x; rkxh[1] = e5.y; rkxh[2] = e5.z; rkxh[3] = e5.w;
@@ -320,15 +357,17 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
 }
 
 template <bool EDGE>
-__device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane)
+__device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane,
+                                                const unsigned smem_warp, const float4 *ring_ptr)
 {
+    constexpr int NST = EDGE ? FR_NST_E : FR_NST_I;
     const Dims &d = a.d;
     FwdCtx k;
     k.ld = d.ldx; k.nzA = d.nzA; k.nPml = d.nPml; k.fsz = d.fsz;
     const size_t fsz = d.fsz;
     const int p = sa.it & 1;
     float *st = slot_state(a, s);
-    k.xq0 = wk.x - 4 + 4 * lane;                 // true first column of this lane's quad
+    k.xq0 = wk.x - 4 + 4 * lane;                           // true first column of this lane's quad
     const bool colok = (k.xq0 >= 0) && (k.xq0 < d.ldx);
     const int xq = colok ? k.xq0 : 0;                      // lanes outside the array read column 0; their values feed inactive cells only
     k.g = st + (size_t)(p ? S_FWD1 : S_FWD) * fsz + xq;
@@ -343,6 +382,7 @@ __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs
     k.lown = (lane >= 1) && (lane <= 30) && colok;
     k.zs = a.t.zs[s]; k.xs = a.t.xs[s];
     k.c1z = d.c1z; k.c2z = d.c2z; k.c1x = d.c1x; k.c2x = d.c2x; k.dt = d.dt;
+    k.ring_s = smem_warp + lane * 16; k.ring_p = ring_ptr + lane;
     // EDGE: active columns of the quad (x in [2, nx-3]) and whether the quad touches the x CPML strips
     k.amask = 0xf; k.xps = false; k.xpv = false;
     if (EDGE) {
@@ -363,33 +403,31 @@ __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs
 #pragma unroll
     for (int j = 0; j < 6; j++) { w.vz[j] = w.vx[j] = w.zz[j] = w.xz[j] = w.xx[j] = zero; }
     auto rowoff = [&](int row) { return (size_t)min(max(row, 0), d.nzA - 1) * d.ldx; };
-    // v rows zc0-4 .. zc0 -> slots 0..4 ; row rho lives in slot (rho - (zc0-4)) % 6   (edge warps load row zc0 in the first iteration)
+    const int r0 = k.zc0 - 2;
+    // v rows r0-2 .. r0+1 -> slots 0..3 ; row rho lives in slot (rho - (zc0-4)) % 6 ; row r+2 arrives through the ring
 #pragma unroll
-    for (int j = 0; j < (EDGE ? 4 : 5); j++) {
-        const size_t ro = rowoff(k.zc0 - 4 + j);
+    for (int j = 0; j < 4; j++) {
+        const size_t ro = rowoff(r0 - 2 + j);
         w.vz[j] = ldq(k.g + F_VZ * fsz + ro); w.vx[j] = ldq(k.g + F_VX * fsz + ro);
     }
-    w.ozz[0] = w.oxz[0] = w.oxx[0] = w.lam[0] = w.mu[0] = w.mua[0] = w.bya[0] = w.byb[0] = zero;
-    w.ozz[1] = w.oxz[1] = w.oxx[1] = w.lam[1] = w.mu[1] = w.mua[1] = w.bya[1] = w.byb[1] = zero;
-    if (!EDGE) {
-        const size_t ro = rowoff(k.zc0 - 2);
-        w.ozz[0] = ldq(k.g + F_SZZ * fsz + ro); w.oxz[0] = ldq(k.g + F_SXZ * fsz + ro); w.oxx[0] = ldq(k.g + F_SXX * fsz + ro);
-        w.lam[0] = ldq(k.m + M_LAM * fsz + ro); w.mu[0] = ldq(k.m + M_MU * fsz + ro); w.mua[0] = ldq(k.m + M_MUAVE * fsz + ro);
-    }
+#pragma unroll
+    for (int j = 0; j < NST - 1; j++) stream_fwd_issue<EDGE>(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
     if (!EDGE) {
         // interior: rotate the windows by full unrolling (6 rows per trip); surplus rows of the last trip are computed and dropped
 #pragma unroll 1
         for (int kk = 0; kk < niter; kk += 6) {
-            const int r = k.zc0 - 2 + kk;
-            stream_fwd_row<EDGE, 0>(k, w, r);     stream_fwd_row<EDGE, 1>(k, w, r + 1); stream_fwd_row<EDGE, 2>(k, w, r + 2);
-            stream_fwd_row<EDGE, 3>(k, w, r + 3); stream_fwd_row<EDGE, 4>(k, w, r + 4); stream_fwd_row<EDGE, 5>(k, w, r + 5);
+            const int r = r0 + kk;
+            stream_fwd_row<EDGE, 0>(k, w, r, 0 % NST);     stream_fwd_row<EDGE, 1>(k, w, r + 1, 1 % NST); stream_fwd_row<EDGE, 2>(k, w, r + 2, 2 % NST);
+            stream_fwd_row<EDGE, 3>(k, w, r + 3, 3 % NST); stream_fwd_row<EDGE, 4>(k, w, r + 4, 4 % NST); stream_fwd_row<EDGE, 5>(k, w, r + 5, 5 % NST);
         }
     } else {
         // edge: one row per trip and explicit register moves, so the (much longer) body stays resident in the instruction cache
+        int stage = 0;
 #pragma unroll 1
         for (int kk = 0; kk < niter; kk++) {
-            stream_fwd_row<EDGE, 0>(k, w, k.zc0 - 2 + kk);
+            stream_fwd_row<EDGE, 0>(k, w, r0 + kk, stage);
+            stage = stage == NST - 1 ? 0 : stage + 1;
 #pragma unroll
             for (int j = 0; j < 4; j++) { w.vz[j] = w.vz[j + 1]; w.vx[j] = w.vx[j + 1]; }
             w.zz[3] = w.zz[4]; w.zz[4] = w.zz[5]; w.zz[5] = w.zz[0];
@@ -397,28 +435,28 @@ __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs
             w.xx[4] = w.xx[5]; w.xx[5] = w.xx[0];
         }
     }
+    cp_wait<0>();
 }
-
-// the CPML / rim variant is compiled out of line so that its extra live state cannot spill the interior loop
-__device__ __forceinline__ void stream_fwd_edge(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane)
-{ stream_fwd_body<true>(a, sa, s, wk, lane); }
 
 #ifndef SW_MINB
 #define SW_MINB 2
 #endif
-// grid: x = nAux + ceil(nWork / SW_WPB), y = slot
+// grid: x = nAux + ceil(nWork / SW_WPB), y = slot ; dynamic shared memory FR_SMEM
 __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_fwd(const KArgs a, const StreamArgs sa)
 {
+    extern __shared__ __align__(16) float smem[];
     pdl_launch_dependents();
     const int s = blockIdx.y;
     if ((int)blockIdx.x < sa.nAux) { pdl_wait(); stream_fwd_aux(a, sa, s); return; }
     const int wg = ((int)blockIdx.x - sa.nAux) * SW_WPB + ((int)threadIdx.x >> 5);
     if (wg >= sa.nWork) return;      // whole warp leaves (the in-place CPML memory must not be updated twice)
     const int4 wk = __ldg(sa.work + wg);
-    pdl_wait();
     const int lane = threadIdx.x & 31;
-    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_fwd_body<false>(a, sa, s, wk, lane);
-    else stream_fwd_edge(a, sa, s, wk, lane);
+    const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * FR_WARP_BYTES;
+    const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (FR_WARP_BYTES / 16);
+    pdl_wait();
+    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_fwd_body<false>(a, sa, s, wk, lane, sw, sp);
+    else stream_fwd_body<true>(a, sa, s, wk, lane, sw, sp);
 }
 
 // ================================================================================================
@@ -834,14 +872,6 @@ constexpr int RC_WARP_BYTES = RC_NST * RC_NARR * 512;       // 27 KB per warp
 constexpr size_t RC_SMEM = (size_t)SW_WPB * RC_WARP_BYTES;  // 108 KB per CTA, 2 CTAs per SM
 enum { RA_SZZ = 0, RA_SXZ, RA_SXX, RA_OVZ, RA_OVX, RA_AVZ, RA_AVX, RA_BA, RA_BB, RA_GR,      // rows r+2, r+1, r, then row r
        RA_ASZZ, RA_ASXZ, RA_ASXX, RA_LAM, RA_MU, RA_MUA, RA_GL, RA_GM };                        // row r-2
-
-#ifndef RC_CP_OP
-#define RC_CP_OP "cp.async.ca.shared.global"
-#endif
-__device__ __forceinline__ void cp16(unsigned saddr, const float *g)
-{ asm volatile(RC_CP_OP " [%0], [%1], 16;" ::"r"(saddr), "l"(g)); }
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct RecCtx {
     const float *g, *adj, *m, *ringb, *amp;

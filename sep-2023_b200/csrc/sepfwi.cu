@@ -348,6 +348,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         CU(cudaFuncSetAttribute(k_fused_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
         CU(cudaFuncSetAttribute(k_fused_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
         CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
+        CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
     }
     size_t of = 0;
     auto takef = [&](size_t n) { size_t o = of; of += n; return o; };
@@ -704,7 +705,7 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
         for (int it = 0; it <= d.nSteps - 2; it++) {
             const bool pr = it < h->prof_steps;
             sa.it = it; sa.mask = (it >= 1 && mrec > 0) ? mask : 0;
-            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), 0, st, h->pdl, a, sa)));
+            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), FR_SMEM, st, h->pdl, a, sa)));
         }
         const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state
         if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, false, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, d.nSteps - 1, mask, h->p.fiber, par)));
