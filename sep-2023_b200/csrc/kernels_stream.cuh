@@ -472,6 +472,8 @@ struct AdjCtx {
     const int *injList;      // -> index into injCell / injField / injPtr of the slot tables
     const SlotTab *t;
     float *stage;            // per-warp shared staging row: [2][128] floats (vz, vx increments by column)
+    const float4 *ring_p;    // this lane's 16 bytes of ring stage 0, array 0
+    unsigned ring_s;
     size_t fsz, tb, cb;
     int ld, nzA, nx, nPml, zc0, zc1, xq0, lane, s, nSteps;
     unsigned amask;
@@ -480,10 +482,14 @@ struct AdjCtx {
     float c1z, c2z, c1x, c2x, dt;
 };
 struct AdjWin {
-    float4 sz[6], sx[6], sxz[6];      // old adjoint stresses, rows r-2 .. r+3
+    float4 sz[6], sx[6], sxz[6];      // old adjoint stresses, rows r-2 .. r+2
     float4 vz[6], vx[6];              // new adjoint velocities, rows r-4 .. r
-    float4 ovz[2], ovx[2], lam[2], mu[2], mua[2], bya[2], byb[2];
 };
+// operand ring (same scheme as the forward kernel): ten row quads per iteration, requested AR_NST-1 rows ahead
+constexpr int AR_NARR = 10, AR_NST = 3;
+constexpr int AR_WARP_BYTES = AR_NARR * AR_NST * 512;          // 15 KB per warp
+constexpr size_t AR_SMEM = (size_t)SW_WPB * AR_WARP_BYTES;     // 60 KB per CTA
+enum { AA_SZ = 0, AA_SX, AA_SXZ, AA_OVZ, AA_OVX, AA_LAM, AA_MU, AA_MUA, AA_BYA, AA_BYB };   // rows r+2 (stresses), r, r-2 (buoyancies)
 
 // residual injection into the freshly updated adjoint velocities of row r (all 128 columns of the warp)
 __device__ __forceinline__ void stream_adj_inject(const AdjCtx &k, const int r, float nvz[4], float nvx[4])
@@ -514,28 +520,32 @@ __device__ __forceinline__ void stream_adj_inject(const AdjCtx &k, const int r, 
     __syncwarp();
 }
 
+// request the operands of the iteration whose phase-A row is r
+__device__ __forceinline__ void stream_adj_issue(const AdjCtx &k, const int r, const int stage)
+{
+    const int ld = k.ld, nzA = k.nzA;
+    const size_t fsz = k.fsz;
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };
+    const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
+    const unsigned sb = k.ring_s + (unsigned)stage * (AR_NARR * 512);
+    cp16(sb + AA_SZ * 512, k.g + F_SZZ * fsz + r2); cp16(sb + AA_SX * 512, k.g + F_SXX * fsz + r2); cp16(sb + AA_SXZ * 512, k.g + F_SXZ * fsz + r2);
+    cp16(sb + AA_OVZ * 512, k.g + F_VZ * fsz + r0); cp16(sb + AA_OVX * 512, k.g + F_VX * fsz + r0);
+    cp16(sb + AA_LAM * 512, k.m + M_LAM * fsz + r0); cp16(sb + AA_MU * 512, k.m + M_MU * fsz + r0); cp16(sb + AA_MUA * 512, k.m + M_MUAVE * fsz + r0);
+    cp16(sb + AA_BYA * 512, k.m + M_BYCA * fsz + rq); cp16(sb + AA_BYB * 512, k.m + M_BYCB * fsz + rq);
+    cp_commit();
+}
+
 template <bool EDGE, int U>
-__device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const int r)
+__device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const int r, const int stage)
 {
     const int ld = k.ld, nzA = k.nzA;
     const size_t fsz = k.fsz;
     const float c1z = k.c1z, c2z = k.c2z, c1x = k.c1x, c2x = k.c2x, dt = k.dt;
     constexpr int u = U;
-    constexpr int cb = u & 1, nb = cb ^ 1;
-    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };
-    if (!EDGE) {
-        const size_t r3 = rowoff(r + 3), r1 = rowoff(r + 1), rq = rowoff(r - 1);
-        w.sz[(u + 5) % 6] = ldq(k.g + F_SZZ * fsz + r3); w.sx[(u + 5) % 6] = ldq(k.g + F_SXX * fsz + r3); w.sxz[(u + 5) % 6] = ldq(k.g + F_SXZ * fsz + r3);
-        w.ovz[nb] = ldq(k.g + F_VZ * fsz + r1); w.ovx[nb] = ldq(k.g + F_VX * fsz + r1);
-        w.lam[nb] = ldq(k.m + M_LAM * fsz + r1); w.mu[nb] = ldq(k.m + M_MU * fsz + r1); w.mua[nb] = ldq(k.m + M_MUAVE * fsz + r1);
-        w.bya[nb] = ldq(k.m + M_BYCA * fsz + rq); w.byb[nb] = ldq(k.m + M_BYCB * fsz + rq);
-    } else {
-        const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
-        w.sz[(u + 4) % 6] = ldq(k.g + F_SZZ * fsz + r2); w.sx[(u + 4) % 6] = ldq(k.g + F_SXX * fsz + r2); w.sxz[(u + 4) % 6] = ldq(k.g + F_SXZ * fsz + r2);
-        w.ovz[cb] = ldq(k.g + F_VZ * fsz + r0); w.ovx[cb] = ldq(k.g + F_VX * fsz + r0);
-        w.lam[cb] = ldq(k.m + M_LAM * fsz + r0); w.mu[cb] = ldq(k.m + M_MU * fsz + r0); w.mua[cb] = ldq(k.m + M_MUAVE * fsz + r0);
-        w.bya[cb] = ldq(k.m + M_BYCA * fsz + rq); w.byb[cb] = ldq(k.m + M_BYCB * fsz + rq);
-    }
+    stream_adj_issue(k, r + (AR_NST - 1), stage == 0 ? AR_NST - 1 : stage - 1);
+    cp_wait<AR_NST - 1>();
+    const float4 *sb = k.ring_p + stage * (AR_NARR * 32);
+    w.sz[(u + 4) % 6] = sb[AA_SZ * 32]; w.sx[(u + 4) % 6] = sb[AA_SX * 32]; w.sxz[(u + 4) % 6] = sb[AA_SXZ * 32];     // row r+2
     // ---- phase A: adjoint velocities at row r from the old adjoint stresses, rows r-2 .. r+2 (slots u .. u+4)
     {
         const float4 z1 = w.sz[(u + 1) % 6], z2 = w.sz[(u + 2) % 6], z3 = w.sz[(u + 3) % 6], z4 = w.sz[(u + 4) % 6];
@@ -545,8 +555,9 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
         const float zm1[4] = Q4(z1), zc0[4] = Q4(z2), zp1[4] = Q4(z3), zp2[4] = Q4(z4);
         const float xm1[4] = Q4(x1), xc0[4] = Q4(x2), xp1[4] = Q4(x3), xp2[4] = Q4(x4);
         const float m2[4] = Q4(q0), m1[4] = Q4(q1), c0[4] = Q4(q2), p1[4] = Q4(q3);
-        const float l[4] = Q4(w.lam[cb]), mm[4] = Q4(w.mu[cb]), ma[4] = Q4(w.mua[cb]);
-        const float ovz[4] = Q4(w.ovz[cb]), ovx[4] = Q4(w.ovx[cb]);
+        const float4 lam4 = sb[AA_LAM * 32], mu4 = sb[AA_MU * 32], mua4 = sb[AA_MUA * 32], ovz4 = sb[AA_OVZ * 32], ovx4 = sb[AA_OVX * 32];
+        const float l[4] = Q4(lam4), mm[4] = Q4(mu4), ma[4] = Q4(mua4);
+        const float ovz[4] = Q4(ovz4), ovx[4] = Q4(ovx4);
         float nvz[4], nvx[4];
         const bool rown = (r >= k.zc0) && (r < k.zc1);
         const size_t ro = (size_t)r * ld;
@@ -651,7 +662,8 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
         const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
         const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
         const float ozz[4] = Q4(w.sz[u % 6]), oxx[4] = Q4(w.sx[u % 6]), oxz[4] = Q4(w.sxz[u % 6]);     // old stresses of row r-2 live in slot u
-        const float ba[4] = Q4(w.bya[cb]), bb[4] = Q4(w.byb[cb]);
+        const float4 bya4 = sb[AA_BYA * 32], byb4 = sb[AA_BYB * 32];
+        const float ba[4] = Q4(bya4), bb[4] = Q4(byb4);
         float nzz[4], nxz[4], nxx[4];
         const bool qown = (q >= k.zc0) && (q < k.zc1);
         const size_t ro = (size_t)q * ld;
@@ -743,10 +755,12 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
 }
 
 template <bool EDGE>
-__device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, float *stage)
+__device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, float *stage,
+                                                const unsigned smem_warp, const float4 *ring_ptr)
 {
     const Dims &d = a.d;
     AdjCtx k;
+    k.ring_s = smem_warp + lane * 16; k.ring_p = ring_ptr + lane;
     k.ld = d.ldx; k.nzA = d.nzA; k.nx = d.nx; k.nPml = d.nPml; k.fsz = d.fsz; k.lane = lane; k.s = s; k.nSteps = d.nSteps;
     const size_t fsz = d.fsz;
     float *st = slot_state(a, s);
@@ -791,45 +805,43 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
 #pragma unroll
     for (int j = 0; j < 6; j++) { w.sz[j] = w.sx[j] = w.sxz[j] = w.vz[j] = w.vx[j] = zero; }
     auto rowoff = [&](int row) { return (size_t)min(max(row, 0), d.nzA - 1) * d.ldx; };
+    const int r0 = k.zc0 - 2;
 #pragma unroll
-    for (int j = 0; j < (EDGE ? 4 : 5); j++) {
-        const size_t ro = rowoff(k.zc0 - 4 + j);
+    for (int j = 0; j < 4; j++) {       // rows r0-2 .. r0+1 ; row r+2 arrives through the ring
+        const size_t ro = rowoff(r0 - 2 + j);
         w.sz[j] = ldq(k.g + F_SZZ * fsz + ro); w.sx[j] = ldq(k.g + F_SXX * fsz + ro); w.sxz[j] = ldq(k.g + F_SXZ * fsz + ro);
     }
-    w.ovz[0] = w.ovx[0] = w.lam[0] = w.mu[0] = w.mua[0] = w.bya[0] = w.byb[0] = zero;
-    w.ovz[1] = w.ovx[1] = w.lam[1] = w.mu[1] = w.mua[1] = w.bya[1] = w.byb[1] = zero;
-    if (!EDGE) {
-        const size_t ro = rowoff(k.zc0 - 2);
-        w.ovz[0] = ldq(k.g + F_VZ * fsz + ro); w.ovx[0] = ldq(k.g + F_VX * fsz + ro);
-        w.lam[0] = ldq(k.m + M_LAM * fsz + ro); w.mu[0] = ldq(k.m + M_MU * fsz + ro); w.mua[0] = ldq(k.m + M_MUAVE * fsz + ro);
-    }
+#pragma unroll
+    for (int j = 0; j < AR_NST - 1; j++) stream_adj_issue(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
     if (!EDGE) {
 #pragma unroll 1
         for (int kk = 0; kk < niter; kk += 6) {
-            const int r = k.zc0 - 2 + kk;
-            stream_adj_row<EDGE, 0>(k, w, r);     stream_adj_row<EDGE, 1>(k, w, r + 1); stream_adj_row<EDGE, 2>(k, w, r + 2);
-            stream_adj_row<EDGE, 3>(k, w, r + 3); stream_adj_row<EDGE, 4>(k, w, r + 4); stream_adj_row<EDGE, 5>(k, w, r + 5);
+            const int r = r0 + kk;
+            stream_adj_row<EDGE, 0>(k, w, r, 0 % AR_NST);     stream_adj_row<EDGE, 1>(k, w, r + 1, 1 % AR_NST); stream_adj_row<EDGE, 2>(k, w, r + 2, 2 % AR_NST);
+            stream_adj_row<EDGE, 3>(k, w, r + 3, 3 % AR_NST); stream_adj_row<EDGE, 4>(k, w, r + 4, 4 % AR_NST); stream_adj_row<EDGE, 5>(k, w, r + 5, 5 % AR_NST);
         }
     } else {
+        int stg = 0;
 #pragma unroll 1
         for (int kk = 0; kk < niter; kk++) {
-            stream_adj_row<EDGE, 0>(k, w, k.zc0 - 2 + kk);
+            stream_adj_row<EDGE, 0>(k, w, r0 + kk, stg);
+            stg = stg == AR_NST - 1 ? 0 : stg + 1;
 #pragma unroll
             for (int j = 0; j < 4; j++) { w.sz[j] = w.sz[j + 1]; w.sx[j] = w.sx[j + 1]; w.sxz[j] = w.sxz[j + 1]; }
             w.vz[2] = w.vz[3]; w.vz[3] = w.vz[4]; w.vz[4] = w.vz[5]; w.vz[5] = w.vz[0];
             w.vx[3] = w.vx[4]; w.vx[4] = w.vx[5]; w.vx[5] = w.vx[0];
         }
     }
+    cp_wait<0>();
 }
 
-__device__ __forceinline__ void stream_adj_edge(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane, float *stage)
-{ stream_adj_body<true>(a, sa, s, wk, lane, stage); }
 
 // grid: x = 1 + ceil(nWork / SW_WPB), y = slot ; CTA 0 writes the stf gradient
 __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, const StreamArgs sa)
 {
     __shared__ __align__(16) float stage[SW_WPB][256];
+    extern __shared__ __align__(16) float smem[];
     pdl_launch_dependents();
     const int s = blockIdx.y;
     const Dims &d = a.d;
@@ -846,9 +858,11 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, co
     if (wg >= sa.nWork) return;
     const int4 wk = __ldg(sa.work + wg);
     const int lane = threadIdx.x & 31;
+    const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * AR_WARP_BYTES;
+    const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (AR_WARP_BYTES / 16);
     pdl_wait();
-    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_adj_body<false>(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
-    else stream_adj_edge(a, sa, s, wk, lane, stage[threadIdx.x >> 5]);
+    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_adj_body<false>(a, sa, s, wk, lane, stage[threadIdx.x >> 5], sw, sp);
+    else stream_adj_body<true>(a, sa, s, wk, lane, stage[threadIdx.x >> 5], sw, sp);
 }
 
 // ================================================================================================

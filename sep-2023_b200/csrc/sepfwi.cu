@@ -349,6 +349,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         CU(cudaFuncSetAttribute(k_fused_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
         CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
         CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
+        CU(cudaFuncSetAttribute(k_stream_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AR_SMEM));
     }
     size_t of = 0;
     auto takef = [&](size_t n) { size_t o = of; of += n; return o; };
@@ -811,7 +812,7 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
             LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F4_NT, R_SMEM, st>>>(a, fa)));
             if (h->stream) {
                 sa.it = it; sa.q = q; sa.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (launch_pdl(k_stream_adj, sagrd, dim3(SW_NT), 0, st, h->pdl, a, sa)));
+                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (launch_pdl(k_stream_adj, sagrd, dim3(SW_NT), AR_SMEM, st, h->pdl, a, sa)));
             } else
             LAUNCH(h, SEPFWI_K_FUSED_ADJ, pr, st, (k_fused_adj<<<agrd, F4_NT, A_SMEM, st>>>(a, fa)));
             q ^= 1; pa ^= 1;
