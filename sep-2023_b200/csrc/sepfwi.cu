@@ -68,8 +68,8 @@ struct sepfwi_handle {
     bool stream = false;   // register-streaming kernels (kernels = 0)
     int nSM = 148;
     bool pdl = true;       // programmatic dependent launch inside the time loops (SEPFWI_PDL=0 disables)
-    int4 *work = nullptr;  // work list of the streaming kernels (device)
-    size_t work_cap = 0;
+    int4 *work[3] = {nullptr, nullptr, nullptr};   // work lists of the streaming kernels (device): forward, reconstruction, adjoint
+    size_t work_cap[3] = {0, 0, 0};
     size_t o_amp, o_rxz, o_w, o_injCoef;
     bool use_w = false;
     // host copies
@@ -258,7 +258,7 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
                    h->dense[0], h->dense[1], h->dense[2], h->t_flt};
     for (float *q : fp) if (q) cudaFree(q);
     if (h->maxcp) cudaFree(h->maxcp);
-    if (h->work) cudaFree(h->work);
+    for (int k = 0; k < 3; k++) if (h->work[k]) cudaFree(h->work[k]);
     if (h->partial) cudaFree(h->partial);
     if (h->misfit) cudaFree(h->misfit);
     if (h->t_int) cudaFree(h->t_int);
@@ -627,7 +627,7 @@ static int max_nrec(int nb, const sepfwi_shot *shots)
 //     CPML memory variables, no look-ahead): they get shorter chunks and are listed first so they never form the tail;
 //   * interior chunks are Lz rows with (Lz + 4) a multiple of the 6-row unroll, Lz chosen so that the item count fills whole
 //     waves of nSM x 8 resident warps (2 CTAs x 4 warps at 255 registers).  SEPFWI_LZ / SEPFWI_LZE override the two heights.
-static int stream_plan(sepfwi_handle *h, int nb, StreamArgs &sa)
+static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 adj*/, StreamArgs &sa)
 {
     const Dims &d = h->d;
     memset(&sa, 0, sizeof(sa));
@@ -637,24 +637,37 @@ static int stream_plan(sepfwi_handle *h, int nb, StreamArgs &sa)
     // the branch-free variants need a margin of nPml + 5
     const int zi0 = d.nPml + 5, zi1 = d.nzA - d.nPml - 5;
     const double conc = (double)h->nSM * 2 * SW_WPB;
-    const double edge_cost = 1.8;
     auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 3 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 4; };
     int nInnerStrips = 0;
     for (int sx = 0; sx < nStrips; sx++) nInnerStrips += strip_inner(sx) ? 1 : 0;
-    int best = 8;
+    // cost model: whole waves of `conc` warps, each wave as long as its longest item.  Interior items run
+    // 6 ceil((Lz+4)/6) rows, edge items Le + 4 rows at edge_cost x the cost per row.
+    // measured cost of an edge row relative to an interior row: in throughput (many waves, HBM-bound) and in latency
+    // (a lone warp per scheduler: shorter look-ahead, register moves); the CPML rows of the adjoint sweep are the expensive ones
+    static const double edge_thr[3] = {1.15, 1.1, 1.8}, edge_lat[3] = {2.0, 1.6, 2.5};
+    const double edge_cost = edge_thr[which], edge_latc = edge_lat[which];
+    auto counts = [&](int Lz, int Le, double &n_in, double &n_ed) {
+        const int nch = (zi1 - zi0 + Lz - 1) / Lz, nche = (zi1 - zi0 + Le - 1) / Le, ntb = 2 * ((zi0 + Le - 1) / Le);
+        n_in = (double)nInnerStrips * nch;
+        n_ed = (double)(nStrips - nInnerStrips) * nche + (double)nStrips * ntb;
+    };
+    int best = 8, Le = 8;
     double bestc = 1e300;
-    for (int Lz = 8; Lz <= 128; Lz += 6) {
-        const int nch = (zi1 - zi0 + Lz - 1) / Lz;
-        const int Le = std::max(4, (int)((Lz + 4) / edge_cost) - 4);
-        const int nche = (zi1 - zi0 + Le - 1) / Le, ntb = 2 * ((zi0 + Le - 1) / Le);
-        const double items = (double)nInnerStrips * nch + (double)(nStrips - nInnerStrips) * nche + (double)nStrips * ntb;
-        const double c = ceil(items * nb / conc) * (Lz + 4 + 3);
-        if (c < bestc) { bestc = c; best = Lz; }
-    }
+    static const int les[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128};
+    for (int Lz = 2; Lz <= 128; Lz += 6)
+        for (int le : les) {
+            double n_in, n_ed;
+            counts(Lz, le, n_in, n_ed);
+            const double it_i = 6 * ((Lz + 4 + 5) / 6) + 3.0, it_e = (le + 4 + 3.0) * edge_cost;   // rows per item (+3: prologue)
+            const double work = (n_in * it_i + n_ed * it_e) * nb / conc, longest = std::max(it_i, (le + 4 + 3.0) * edge_latc);
+            // one wave or less: the longest item is the time; many waves: throughput plus half an item of tail
+            const double c = std::max(longest, work + 0.5 * longest);
+            if (c < bestc - 1e-9) { bestc = c; best = Lz; Le = le; }
+        }
     if (const char *e = getenv("SEPFWI_LZ")) { const int v = atoi(e); if (v >= 2) best = v; }
-    int Le = std::max(4, (int)((best + 4) / edge_cost) - 4);
     if (const char *e = getenv("SEPFWI_LZE")) { const int v = atoi(e); if (v >= 2) Le = v; }
     if (const char *e = getenv("SEPFWI_FORCE")) sa.force = atoi(e);
+    if (getenv("SEPFWI_PLAN_DEBUG")) fprintf(stderr, "stream_plan[%d]: nb %d Lz %d Le %d (%.0f) cost %.1f\n", which, nb, best, Le, 0.0, bestc);
     std::vector<int4> edge, inner;
     auto split = [&](int z0, int z1, int L, int sx, bool is_edge) {
         const int n = (z1 - z0 + L - 1) / L;
@@ -671,14 +684,14 @@ static int stream_plan(sepfwi_handle *h, int nb, StreamArgs &sa)
     // interior items: chunk-major so that concurrently running warps read neighbouring strips of the same rows
     std::stable_sort(inner.begin(), inner.end(), [](const int4 &p, const int4 &q) { return p.y < q.y; });
     edge.insert(edge.end(), inner.begin(), inner.end());
-    if (edge.size() > h->work_cap) {
-        if (h->work) cudaFree(h->work);
-        h->work = nullptr; h->work_cap = 0;
-        CU(cudaMalloc((void **)&h->work, edge.size() * sizeof(int4)));
-        h->work_cap = edge.size();
+    if (edge.size() > h->work_cap[which]) {
+        if (h->work[which]) cudaFree(h->work[which]);
+        h->work[which] = nullptr; h->work_cap[which] = 0;
+        CU(cudaMalloc((void **)&h->work[which], edge.size() * sizeof(int4)));
+        h->work_cap[which] = edge.size();
     }
-    CU(cudaMemcpy(h->work, edge.data(), edge.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    sa.work = h->work; sa.nWork = (int)edge.size();
+    CU(cudaMemcpy(h->work[which], edge.data(), edge.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    sa.work = h->work[which]; sa.nWork = (int)edge.size();
     return 0;
 }
 
@@ -697,7 +710,7 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
     CU(cudaEventRecord(h->ev[0], st));
     if (h->stream) {
         StreamArgs sa;
-        int rc = stream_plan(h, nb, sa);
+        int rc = stream_plan(h, nb, 0, sa);
         if (rc) return rc;
         sa.fiber = h->p.fiber; sa.save_ring = save_ring ? 1 : 0; sa.nrecMax = mrec;
         const int items = (mrec > 0 ? mrec : 0) + (save_ring ? d.ringLen : 0);
@@ -793,8 +806,8 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     dim3 rgrd((rx + BX - 1) / BX, (rz + BY - 1) / BY, nb);
     dim3 igrd((minj + 127) / 128, nb);
     CU(cudaEventRecord(h->ev[2], st));
-    StreamArgs sa;
-    if (h->stream) { int rc = stream_plan(h, nb, sa); if (rc) return rc; }
+    StreamArgs sa, sr;
+    if (h->stream) { int rc = stream_plan(h, nb, 2, sa); if (rc) return rc; rc = stream_plan(h, nb, 1, sr); if (rc) return rc; }
     if (h->fused) {
         dim3 agrd(h->ntx, h->ntz, nb);
         dim3 sagrd(1 + (sa.nWork + SW_WPB - 1) / SW_WPB, nb);
@@ -806,8 +819,8 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
             FusedBwdArgs fa;
             fa.it = it; fa.q = q; fa.pa = pa;
             if (h->stream && !getenv("SEPFWI_TILE_RECON")) {
-                sa.it = it; sa.q = q; sa.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (launch_pdl(k_stream_recon, dim3((sa.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM, st, h->pdl, a, sa)));
+                sr.it = it; sr.q = q; sr.pa = pa;
+                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (launch_pdl(k_stream_recon, dim3((sr.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM, st, h->pdl, a, sr)));
             } else
             LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F4_NT, R_SMEM, st>>>(a, fa)));
             if (h->stream) {
