@@ -283,11 +283,18 @@ def main():
 
     fwd_kernels = [k for k in ("stream_fwd", "fused_fwd", "stress_fwd", "velocity_fwd") if k in prof]
     t_fwd_step = sum(avg(k) for k in fwd_kernels) * 1e-3
+    traffic = None      # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(w["name"], {})
+        if fwd_kernels and all(k in tr for k in fwd_kernels):
+            traffic = float(sum(tr[k] for k in fwd_kernels))
+    except Exception:
+        pass
     roof = None
     if t_fwd_step > 0:
         ach = B_FWD * w["live"] / t_fwd_step / 1e9
         roof = {"bound": "hbm", "kernel": "+".join(fwd_kernels), "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": B_FWD * w["live"], "avg_launch_us": t_fwd_step * 1e6,
                 "note": "one forward time step = %s; working set %.0f MB (%s the 126 MB L2)"
                         % ("+".join(fwd_kernels), 13 * w["live"] * 4 / 1e6, "fits in" if 13 * w["live"] * 4 < 100e6 else "exceeds"),
@@ -419,7 +426,15 @@ def extra_large(args, Propagator, ShotSpec, torch, dev, local, peak):
         tf, tb = sum(us[k] for k in fk) * 1e-6, sum(us[k] for k in bk) * 1e-6
         af = B_FWD * w["live"] / tf / 1e9
         ab = (B_ADJ * w["live"] + B_REC * w["interior"]) / tb / 1e9
-        return {"workload": w["desc"], "per_kernel_us": us,
+        alg = {"stream_fwd": B_FWD * w["live"], "fused_fwd": B_FWD * w["live"], "stream_adj": B_ADJ * w["live"], "fused_adj": B_ADJ * w["live"],
+               "stream_recon": B_REC * w["interior"], "fused_recon": B_REC * w["interior"]}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("c5s", {})
+        except Exception:
+            tr = {}
+        per = {k: {"avg_launch_us": us[k], "algorithmic_bytes_per_launch": alg[k], "achieved_GBs": alg[k] / (us[k] * 1e-6) / 1e9,
+                   "frac": alg[k] / (us[k] * 1e-6) / 1e9 / peak, "traffic": tr.get(k)} for k in us if k in alg}
+        return {"workload": w["desc"], "per_kernel_us": us, "per_kernel_roofline": per,
                 "forward_step": {"kernels": "+".join(fk), "achieved_GBs": af, "frac": af / peak, "cell_updates_per_s": w["live"] / tf},
                 "backward_step": {"kernels": "+".join(bk), "achieved_GBs": ab, "frac": ab / peak, "cell_steps_per_s": w["live"] / tb},
                 "peak_GBs": peak}
