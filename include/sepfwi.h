@@ -69,7 +69,8 @@ typedef struct sepfwi_params {
     int   max_batch;       /* shots propagated concurrently on the device (>= 1)                                       */
     int   max_nrec;        /* upper bound of receivers per shot                                                        */
     int   with_adjoint;    /* 1: allocate boundary store + adjoint state (needed by sepfwi_gradient with_adj)          */
-    int   kernels;         /* 0: default (register-streaming kernels), 1: unfused baseline kernels, 2: shared-memory tile kernels */
+    int   kernels;         /* 0: default (shared-memory-resident forward loop where the tiles of a shot fit the SMs, register-streaming
+                              kernels otherwise), 1: unfused baseline kernels, 2: shared-memory tile kernels, 3: streaming kernels only */
     int   ref_race_compat; /* 0 (default): race-free adjoint source.  1: reproduce the reference's lost update in
                               res_injection_exx/_ezz (utilities.cu:613-614,639-640, launched 32 receivers per block):
                               when receiver 32k subtracts at the cell receiver 32k-1 adds to, the subtraction is dropped.
@@ -139,6 +140,7 @@ int sepfwi_ring_restore(sepfwi_handle *h, float *field, const float *bnd);
  * since creation, and device time of the last forward / backward time loops in ms. */
 int sepfwi_get_cpml(sepfwi_handle *h, int axis /*0=z,1=x*/, float *out6xN);
 long long sepfwi_launch_count(sepfwi_handle *h);
+long long sepfwi_resident_launches(sepfwi_handle *h);   /* cooperative launches of the resident forward loop so far */
 int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
 
 /* Per-kernel device timing: with nsteps > 0 every launch of the first nsteps time steps of each
@@ -146,7 +148,7 @@ int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
  * accumulated milliseconds and launch counts per kernel kind since the last sepfwi_set_profile. */
 enum { SEPFWI_K_RING_SAVE = 0, SEPFWI_K_STRESS_FWD, SEPFWI_K_VELOCITY_FWD, SEPFWI_K_RECORD, SEPFWI_K_VELOCITY_BWD,
        SEPFWI_K_STRESS_BWD, SEPFWI_K_VELOCITY_ADJ, SEPFWI_K_INJECT, SEPFWI_K_STRESS_ADJ, SEPFWI_K_FUSED_FWD,
-       SEPFWI_K_FUSED_RECON, SEPFWI_K_FUSED_ADJ, SEPFWI_K_STREAM_FWD, SEPFWI_K_STREAM_RECON, SEPFWI_K_STREAM_ADJ,
+       SEPFWI_K_FUSED_RECON, SEPFWI_K_FUSED_ADJ, SEPFWI_K_STREAM_FWD, SEPFWI_K_STREAM_RECON, SEPFWI_K_STREAM_ADJ, SEPFWI_K_RESIDENT_FWD,
        SEPFWI_NKERNEL };
 int sepfwi_set_profile(sepfwi_handle *h, int nsteps);
 int sepfwi_get_profile(sepfwi_handle *h, double *ms /*[SEPFWI_NKERNEL]*/, long long *count /*[SEPFWI_NKERNEL]*/);

@@ -21,6 +21,7 @@
 #include "kernels_fused.cuh"
 #include "kernels_fused_bwd.cuh"
 #include "kernels_stream.cuh"
+#include "kernels_resident.cuh"
 
 using namespace sepfwi;
 
@@ -72,6 +73,14 @@ struct sepfwi_handle {
     size_t work_cap[3] = {0, 0, 0};
     size_t o_amp, o_rxz, o_w, o_injCoef;
     bool use_w = false;
+    // shared-memory-resident forward loop (kernels_resident.cuh): used when the tiles of a shot fit the SMs
+    bool resident = false;
+    int *res_dev = nullptr, *res_host = nullptr;    // [flags B*nSM | err | tilePtr B*(nSM+1) | tileRec B*maxRec | ringPtr nSM+1] device / pinned mirror
+    int2 *res_ring = nullptr;                       // [ringLen] ring entries bucketed by tile
+    int res_ring_rpt = 0;                           // tiling the ring entries were built for
+    size_t ro_flags = 0, ro_err = 0, ro_tptr = 0, ro_trec = 0, ro_rptr = 0, res_n = 0;
+    int *res_errh = nullptr;                        // pinned copy of the error flag
+    int res_used = 0;                               // launches of the resident kernel since creation (introspection)
     // host copies
     std::vector<float> hcz, hcx;
     float courant = 0.f;
@@ -90,7 +99,7 @@ struct sepfwi_handle {
 };
 
 static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
-                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_recon", "fused_adj", "stream_fwd", "stream_recon", "stream_adj"};
+                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_recon", "fused_adj", "stream_fwd", "stream_recon", "stream_adj", "resident_fwd"};
 
 // Launch with programmatic stream serialization (the kernels call griddepcontrol.launch_dependents / .wait themselves).
 template <typename... KA, typename... A>
@@ -264,6 +273,10 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
     if (h->t_int) cudaFree(h->t_int);
     if (h->h_int) cudaFreeHost(h->h_int);
     if (h->h_flt) cudaFreeHost(h->h_flt);
+    if (h->res_dev) cudaFree(h->res_dev);
+    if (h->res_ring) cudaFree(h->res_ring);
+    if (h->res_host) cudaFreeHost(h->res_host);
+    if (h->res_errh) cudaFreeHost(h->res_errh);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return 0;
@@ -335,9 +348,9 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     h->nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
     h->o_sInjPtr = takei((size_t)B * h->nStrips * (d.nzA + 1)); h->o_sInj = takei((size_t)B * 2 * maxInj);
     h->n_int = oi;
-    h->stream = !h->sponge && pp->kernels == 0;
+    h->stream = !h->sponge && (pp->kernels == 0 || pp->kernels == 3);
     if (const char *e = getenv("SEPFWI_PDL")) h->pdl = atoi(e) != 0;
-    h->fused = !h->sponge && (pp->kernels == 0 || pp->kernels == 2);
+    h->fused = !h->sponge && (pp->kernels == 0 || pp->kernels == 2 || pp->kernels == 3);
     {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
@@ -350,6 +363,28 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
         CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
         CU(cudaFuncSetAttribute(k_stream_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AR_SMEM));
+    }
+    h->resident = h->stream && pp->kernels == 0 && d.nPml <= RS_PW;
+    if (const char *e = getenv("SEPFWI_RESIDENT")) h->resident = h->resident && atoi(e) != 0;
+    if (h->resident) {
+        int coop = 0;
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        if (!coop) h->resident = false;
+    }
+    if (h->resident) {
+        size_t o = 0;
+        h->ro_flags = o; o += (size_t)B * h->nSM * RS_FLAGW;
+        h->ro_err = o; o += 1;
+        h->ro_tptr = o; o += (size_t)B * (h->nSM + 1);
+        h->ro_trec = o; o += (size_t)B * d.maxRec;
+        h->ro_rptr = o; o += (size_t)h->nSM + 1;
+        h->res_n = o;
+        ALLOC(h->res_dev, o * sizeof(int));
+        ALLOC(h->res_ring, (size_t)std::max(1, d.ringLen) * sizeof(int2));
+        CU(cudaMallocHost((void **)&h->res_host, o * sizeof(int)));
+        CU(cudaMallocHost((void **)&h->res_errh, sizeof(int)));
+        memset(h->res_host, 0, o * sizeof(int));
+        *h->res_errh = 0;
     }
     size_t of = 0;
     auto takef = [&](size_t n) { size_t o = of; of += n; return o; };
@@ -433,6 +468,7 @@ extern "C" int sepfwi_get_cpml(sepfwi_handle *h, int axis, float *out)
 }
 
 extern "C" long long sepfwi_launch_count(sepfwi_handle *h) { return h ? h->launches : 0; }
+extern "C" long long sepfwi_resident_launches(sepfwi_handle *h) { return h ? h->res_used : 0; }
 
 extern "C" int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms)
 {
@@ -695,6 +731,169 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory-resident forward loop (kernels_resident.cuh): tiling plan, tables, cooperative launch.
+struct ResPlan { int rpt = 0, ntx = 0, ntz = 0, orows = 0, per_launch = 0; };
+static int resident_check(sepfwi_handle *h);
+
+template <int RPT>
+static cudaError_t launch_resident(dim3 grid, const KArgs &a, const ResArgs &ra, cudaStream_t st)
+{
+    static bool attr_done[64] = {false};      // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_resident_fwd<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(RPT));
+        if (e != cudaSuccess) return e;
+        attr_done[dev] = true;
+    }
+    void *args[2] = {(void *)&a, (void *)&ra};
+    return cudaLaunchCooperativeKernel((void *)k_resident_fwd<RPT>, grid, dim3(RS_NT), args, rs_smem_bytes(RPT), st);
+}
+
+static const int k_res_rpts[] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13};
+
+// Pick rows-per-thread (tile height 8 RPT - 8) so that the tiles of as many shots as possible are co-resident.
+// Every tile may hold the CPML memory of one z side and one x side only (RS_PW rows / columns each).
+static ResPlan resident_plan(const sepfwi_handle *h, int nb)
+{
+    ResPlan best;
+    if (!h->resident || nb < 1) return best;
+    const Dims &d = h->d;
+    const int ntx = (d.nx + RS_OW - 1) / RS_OW;
+    for (int t = 0; t < ntx; t++) {
+        const int lo = std::max(t * RS_OW - 4, 0), hi = std::min(t * RS_OW + RS_EW - 5, d.nx - 1);
+        if (lo < d.nPml && hi > d.nx - d.nPml - 1) return best;
+    }
+    int forced = 0;
+    if (const char *e = getenv("SEPFWI_RESIDENT_RPT")) forced = atoi(e);
+    double bestc = 1e300;
+    for (int rpt : k_res_rpts) {
+        if (forced && rpt != forced) continue;
+        const int ORmax = 8 * rpt - 8, ER = 8 * rpt, ntz = (d.nzA + ORmax - 1) / ORmax;
+        const int OR = (d.nzA + ntz - 1) / ntz;      // equal tiles
+        const int ctas = ntx * ntz;
+        if (ctas > h->nSM || OR < 4) continue;
+        bool ok = true;
+        for (int t = 0; t < ntz && ok; t++) {
+            const int lo = std::max(t * OR - 4, 0), hi = std::min(t * OR - 4 + ER - 1, d.nzA - 1);
+            if (lo < d.nPml && hi > d.nzA - d.nPml - 1) ok = false;
+        }
+        if (!ok) continue;
+        const int per = std::min(nb, h->nSM / ctas);
+        const int launches = (nb + per - 1) / per;
+        const double c = launches * (1.5 + 0.25 * rpt);     // us per time step: exchange latency + per-row work
+        if (c < bestc) { bestc = c; best.rpt = rpt; best.ntx = ntx; best.ntz = ntz; best.orows = OR; best.per_launch = per; }
+    }
+    if (getenv("SEPFWI_PLAN_DEBUG")) fprintf(stderr, "resident_plan: nb %d -> rpt %d, %d x %d tiles of %d x %d, %d shots per launch\n", nb, best.rpt, best.ntx, best.ntz, best.orows, RS_OW, best.per_launch);
+    return best;
+}
+
+static void ring_cell_host(const Dims &d, int idx, int &z, int &x)       // inverse of the ring map, as kernels_base.cuh ring_cell
+{
+    const int L = 5;
+    if (idx < L * d.nzB) { int j = idx / d.nzB, i = idx - j * d.nzB; z = i + d.nPml - 2; x = j + d.nPml - 2; }
+    else if (idx < 2 * L * d.nzB) { int q = idx - L * d.nzB; int j = q / d.nzB, i = q - j * d.nzB; z = i + d.nPml - 2; x = d.nx - d.nPml - j + 1; }
+    else if (idx < L * (2 * d.nzB + d.nxB)) { int q = idx - 2 * L * d.nzB; int i = q / d.nxB, j = q - i * d.nxB; z = i + d.nPml - 2; x = j + d.nPml - 2; }
+    else { int q = idx - L * (2 * d.nzB + d.nxB); int i = q / d.nxB, j = q - i * d.nxB; z = d.nzA - d.nPml - i + 1; x = j + d.nPml - 2; }
+}
+
+// Whole forward time loop of slots [s0, s0+n) in one cooperative launch.  Expects the state / trace arenas zeroed.
+static int run_resident(sepfwi_handle *h, const ResPlan &pl, int s0, int n, int mask, bool save_ring, cudaStream_t st)
+{
+    const Dims &d = h->d;
+    const int nT = pl.ntx * pl.ntz, OR = pl.orows;
+    int *hp = h->res_host;
+    if (s0 > 0) {       // the pinned tables below are still being read by the previous launch's copy
+        CU(cudaStreamSynchronize(st));
+        int rc = resident_check(h);
+        if (rc) return rc;
+    }
+    // receivers by tile
+    for (int q = 0; q < n; q++) {
+        const int s = s0 + q, nrec = h->h_int[h->o_nrec + s];
+        const int *zr = h->h_int + h->o_zrec + (size_t)s * d.maxRec, *xr = h->h_int + h->o_xrec + (size_t)s * d.maxRec;
+        int *tp = hp + h->ro_tptr + (size_t)q * (nT + 1), *tr = hp + h->ro_trec + (size_t)q * d.maxRec;
+        std::fill(tp, tp + nT + 1, 0);
+        for (int r = 0; r < nrec; r++) tp[(zr[r] / OR) * pl.ntx + xr[r] / RS_OW + 1]++;
+        for (int t = 0; t < nT; t++) tp[t + 1] += tp[t];
+        std::vector<int> cur(tp, tp + nT);
+        for (int r = 0; r < nrec; r++) tr[cur[(zr[r] / OR) * pl.ntx + xr[r] / RS_OW]++] = r;
+    }
+    if (save_ring && h->res_ring_rpt != pl.rpt * 1024 + pl.orows) {
+        std::vector<int> cnt(nT + 1, 0);
+        std::vector<int2> ent(d.ringLen);
+        std::vector<int> own(d.ringLen);
+        for (int idx = 0; idx < d.ringLen; idx++) {
+            int z, x; ring_cell_host(d, idx, z, x);
+            own[idx] = (z / OR) * pl.ntx + x / RS_OW;
+            cnt[own[idx] + 1]++;
+        }
+        for (int t = 0; t < nT; t++) cnt[t + 1] += cnt[t];
+        std::vector<int> cur(cnt.begin(), cnt.end() - 1);
+        for (int idx = 0; idx < d.ringLen; idx++) {
+            int z, x; ring_cell_host(d, idx, z, x);
+            const int t = own[idx], tz0 = (t / pl.ntx) * OR, tx0 = (t % pl.ntx) * RS_OW;
+            ent[cur[t]++] = make_int2(idx, (z - tz0 + 4) * RS_EW + (x - tx0 + 4));
+        }
+        memcpy(hp + h->ro_rptr, cnt.data(), (size_t)(nT + 1) * sizeof(int));
+        CU(cudaMemcpyAsync(h->res_ring, ent.data(), (size_t)d.ringLen * sizeof(int2), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));      // `ent` is a pageable temporary
+        h->res_ring_rpt = pl.rpt * 1024 + pl.orows;
+    }
+    // inboxes: zero, except the slots of neighbours that do not exist; then the error flag
+    for (int q = 0; q < n; q++)
+        for (int t = 0; t < nT; t++) {
+            int *box = hp + h->ro_flags + ((size_t)q * nT + t) * RS_FLAGW;
+            std::fill(box, box + RS_FLAGW, 0);
+            for (int k = 0; k < 9; k++) {
+                const int nz_ = t / pl.ntx + k / 3 - 1, nx_ = t % pl.ntx + k % 3 - 1;
+                if (k != 4 && !(nz_ >= 0 && nz_ < pl.ntz && nx_ >= 0 && nx_ < pl.ntx)) box[k] = 0x7fffffff;
+            }
+        }
+    hp[h->ro_err] = 0;
+    CU(cudaMemcpyAsync(h->res_dev, hp, h->res_n * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (save_ring)      // sigma(0) = 0: the stress rings of time 0 are never written by the kernel
+        for (int q = 0; q < n; q++)
+            for (int f = F_SZZ; f <= F_SXX; f++)
+                CU(cudaMemsetAsync(h->ring + (((size_t)(s0 + q) * NFIELD + f) * d.nSteps) * d.ringLen, 0, (size_t)d.ringLen * sizeof(float), st));
+    KArgs a = kargs(h);
+    ResArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.ntx = pl.ntx; ra.ntz = pl.ntz; ra.orows = pl.orows; ra.slot0 = s0; ra.mask = mask; ra.fiber = h->p.fiber; ra.save_ring = save_ring ? 1 : 0;
+    if (const char *e = getenv("SEPFWI_RES_DEBUG")) ra.dbg = atoi(e);
+    ra.flags = h->res_dev + h->ro_flags; ra.err = h->res_dev + h->ro_err;
+    ra.tilePtr = h->res_dev + h->ro_tptr; ra.tileRec = h->res_dev + h->ro_trec;
+    ra.ringPtr = h->res_dev + h->ro_rptr; ra.ringEnt = h->res_ring;
+    const dim3 grid(nT, n);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (pl.rpt) {
+    case 3: e = launch_resident<3>(grid, a, ra, st); break;
+    case 4: e = launch_resident<4>(grid, a, ra, st); break;
+    case 5: e = launch_resident<5>(grid, a, ra, st); break;
+    case 6: e = launch_resident<6>(grid, a, ra, st); break;
+    case 7: e = launch_resident<7>(grid, a, ra, st); break;
+    case 8: e = launch_resident<8>(grid, a, ra, st); break;
+    case 9: e = launch_resident<9>(grid, a, ra, st); break;
+    case 10: e = launch_resident<10>(grid, a, ra, st); break;
+    case 11: e = launch_resident<11>(grid, a, ra, st); break;
+    case 12: e = launch_resident<12>(grid, a, ra, st); break;
+    case 13: e = launch_resident<13>(grid, a, ra, st); break;
+    }
+    if (e != cudaSuccess) return fail(SEPFWI_ECUDA, "resident forward kernel (RPT %d, %d x %d tiles, %d shots): %s", pl.rpt, pl.ntx, pl.ntz, n, cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(h->res_errh, h->res_dev + h->ro_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    h->res_used++;
+    return 0;
+}
+
+// after the stream has been synchronised: did a tile of the resident kernel give up waiting for a neighbour?
+static int resident_check(sepfwi_handle *h)
+{
+    if (h->res_errh && *h->res_errh) { *h->res_errh = 0; return fail(SEPFWI_ECUDA, "resident forward kernel: a neighbour tile never arrived (co-residency lost)"); }
+    return 0;
+}
+
 // Forward time loop of one batch.  CPML flavour: libCUFD.cu:268-332; sponge: elasticSolver.py:241-276.
 static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_ring, cudaStream_t st)
 {
@@ -708,7 +907,16 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
     dim3 blk(BX, BY), grd((d.nx + BX - 1) / BX, (d.nzA + BY - 1) / BY, nb);
     dim3 rgrd((mrec + 127) / 128, nb), ringgrd((d.ringLen + 255) / 256, nb);
     CU(cudaEventRecord(h->ev[0], st));
-    if (h->stream) {
+    const ResPlan rpl = resident_plan(h, nb);
+    if (rpl.rpt) {
+        // the whole time loop of `per_launch` shots per cooperative launch, tiles resident in shared memory
+        for (int s0 = 0; s0 < nb; s0 += rpl.per_launch) {
+            const bool pr = h->prof_steps > 0;
+            int rc = 0;
+            LAUNCH(h, SEPFWI_K_RESIDENT_FWD, pr, st, (rc = run_resident(h, rpl, s0, std::min(rpl.per_launch, nb - s0), mrec > 0 ? mask : 0, save_ring, st)));
+            if (rc) return rc;
+        }
+    } else if (h->stream) {
         StreamArgs sa;
         int rc = stream_plan(h, nb, 0, sa);
         if (rc) return rc;
@@ -784,6 +992,8 @@ extern "C" int sepfwi_forward(sepfwi_handle *h, int nshots, const sepfwi_shot *s
                                        (size_t)shots[s0 + s].nrec * d.nSteps * sizeof(float), kind, st));
         CU(cudaStreamSynchronize(st));
         prof_collect(h);
+        rc = resident_check(h);
+        if (rc) return rc;
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
         h->fwd_ms += ms;
@@ -895,6 +1105,8 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
         }
         CU(cudaStreamSynchronize(st));
         prof_collect(h);
+        rc = resident_check(h);
+        if (rc) return rc;
         for (int s = 0; s < nb; s++) J += hj[s];
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));

@@ -37,8 +37,8 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_courant", "sepfwi_forward", "sepfwi_gradient", "sepfwi_cufd", "sepfwi_cufd_clear_cache",
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
-           "sepfwi_kernel_name"]
-NKERNEL = 15
+           "sepfwi_kernel_name", "sepfwi_resident_launches"]
+NKERNEL = 16
 
 _lib = None
 
@@ -73,6 +73,8 @@ def lib():
         L.sepfwi_ring_restore.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.sepfwi_get_cpml.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sepfwi_launch_count.argtypes = [C.c_void_p]
+        L.sepfwi_resident_launches.argtypes = [C.c_void_p]
+        L.sepfwi_resident_launches.restype = C.c_longlong
         L.sepfwi_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.sepfwi_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.sepfwi_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]

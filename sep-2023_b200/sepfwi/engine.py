@@ -137,6 +137,11 @@ class Propagator(object):
     def launches(self):
         return int(lib().sepfwi_launch_count(self._h))
 
+    @property
+    def resident_launches(self):
+        """Cooperative launches of the shared-memory-resident forward loop so far (0: the streaming kernels ran)."""
+        return int(lib().sepfwi_resident_launches(self._h))
+
     def last_timing(self):
         f, b = C.c_float(), C.c_float()
         check(lib().sepfwi_last_timing(self._h, C.byref(f), C.byref(b)))

@@ -99,7 +99,7 @@ def test_streaming_kernels_interior_and_seams(fiber, lz, monkeypatch):
     if lz is not None:
         monkeypatch.setenv("SEPFWI_LZ", lz)
     prob = problems.medium(fiber=fiber)
-    _assert_same(_run_both(prob, 0), _run_both(prob, 1), prob.nshots)
+    _assert_same(_run_both(prob, 3), _run_both(prob, 1), prob.nshots)
 
 
 def test_streaming_kernels_general_fiber_weights():
@@ -107,7 +107,46 @@ def test_streaming_kernels_general_fiber_weights():
     prob = problems.medium(nx=250)
     rng = np.random.default_rng(5)
     w = rng.uniform(-1.0, 1.0, (len(prob.x_rec), 3)).astype(np.float32)
-    _assert_same(_run_both(prob, 0, weights=w), _run_both(prob, 1, weights=w), prob.nshots)
+    _assert_same(_run_both(prob, 3, weights=w), _run_both(prob, 1, weights=w), prob.nshots)
+
+
+def _run_resident(prob, batch, weights=None, rpt=None, monkeypatch=None):
+    """Default path; asserts that the shared-memory-resident forward loop really ran (forward AND gradient)."""
+    O, Propagator, ShotSpec = _mods()
+    if rpt is not None:
+        monkeypatch.setenv("SEPFWI_RESIDENT_RPT", str(rpt))
+    with make_prop(Propagator, prob, max_batch=batch, with_adjoint=True, kernels=0) as P:
+        P.set_model(*prob.true)
+        shots = cuda_shots(prob, ShotSpec)
+        if weights is not None:
+            for sh in shots:
+                sh.weights = weights
+        fwd = P.forward(shots)
+        n1 = P.resident_launches
+        P.set_model(*prob.start)
+        g = P.gradient(shots, [f["ett"] for f in fwd])
+        assert n1 > 0 and P.resident_launches > n1, "resident forward loop did not run"
+    return fwd, g
+
+
+@pytest.mark.parametrize("mk,batch,rpt", [(problems.tiny, 2, None), (lambda: problems.tiny(fiber=1), 1, 3),
+                                          (problems.small, 3, None), (problems.small, 1, 5),
+                                          (problems.medium, 2, None), (lambda: problems.medium(fiber=1), 1, 7),
+                                          (lambda: problems.medium(nx=250), 2, 9)])
+def test_resident_forward_loop_matches_baseline(mk, batch, rpt, monkeypatch):
+    """Shared-memory-resident forward loop (one cooperative launch per shot group, neighbour exchange through
+    per-tile step counters) vs the unfused baseline kernels: traces of all four components, and the gradient
+    computed from its boundary ring + final state by the streaming reverse-time kernels.  Tile heights forced
+    through SEPFWI_RESIDENT_RPT cover tiles that lie entirely inside a CPML strip and several shots per launch."""
+    prob = mk()
+    _assert_same(_run_resident(prob, batch, rpt=rpt, monkeypatch=monkeypatch), _run_both(prob, 1, batch=batch), prob.nshots, tol_g=1e-4)
+
+
+def test_resident_forward_general_fiber_weights():
+    prob = problems.medium(nx=250)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(-1.0, 1.0, (len(prob.x_rec), 3)).astype(np.float32)
+    _assert_same(_run_resident(prob, 2, weights=w), _run_both(prob, 1, weights=w), prob.nshots, tol_g=1e-4)
 
 
 def test_tile_kernels_still_match_baseline():
