@@ -227,16 +227,19 @@ __global__ void __launch_bounds__(RS_NT, 1) k_resident_fwd(const KArgs a, const 
         if (e1 > e0) rs_ring_save<ER>(a, ra, F, s, e0, e1, it, F_VZ, F_VX + 1);
         if (scol && !(ra.dbg & 2)) {
             const float *VZ = Fc + F_VZ * FS, *VX = Fc + F_VX * FS;
-            float wz[RPT + 4], wx[RPT + 4];            // rows r0 - 2 .. r0 + RPT + 1 (clamped: the clamped rows only feed masked cells)
-#pragma unroll
-            for (int k = 0; k < RPT + 4; k++) {
+            float wz[RPT + 4], wx[RPT + 5];            // rows r0 - 2 .. r0 + RPT + 1 (clamped: the clamped rows only feed masked cells)
+            auto woff = [&](int k) {
                 int o = (k - 2) * EW;
                 if (k < 2) o = (max(r0 + k - 2, 0) - r0) * EW;
                 if (k >= RPT + 2) o = (min(r0 + k - 2, ER - 1) - r0) * EW;
-                wz[k] = VZ[o]; wx[k] = VX[o];
-            }
+                return o;
+            };
+            // rolling windows: row j uses wz[j .. j+3], wx[j+1 .. j+4]; the entries of row j+1 are requested one row ahead
+#pragma unroll
+            for (int k = 0; k < 4; k++) { wz[k] = VZ[woff(k)]; wx[k + 1] = VX[woff(k + 1)]; }
 #pragma unroll
             for (int j = 0; j < RPT; j++) {
+                if (j + 1 < RPT) { wz[j + 4] = VZ[woff(j + 4)]; wx[j + 5] = VX[woff(j + 5)]; }
                 if (!((smask >> j) & 1u)) continue;
                 const float *vxr = VX + j * EW, *vzr = VZ + j * EW;
                 float dvz_dz = c1z * (wz[j + 2] - wz[j + 1]) - c2z * (wz[j + 3] - wz[j]);
@@ -276,16 +279,14 @@ __global__ void __launch_bounds__(RS_NT, 1) k_resident_fwd(const KArgs a, const 
         if (vcol && !(ra.dbg & 4)) {
             float *vout = st + (size_t)(((it + 1) & 1) ? S_FWD1 : S_FWD) * fsz + ((ptrdiff_t)zb * ld + x);   // only dereferenced for in-grid rows
             const float *ZZ = Fc + F_SZZ * FS, *XZ = Fc + F_SXZ * FS, *XX = Fc + F_SXX * FS;
-            float wzz[RPT + 3], wxz[RPT + 3];          // szz rows r0 - 1 .. r0 + RPT + 1 ; sxz rows r0 - 2 .. r0 + RPT
+            float wzz[RPT + 4], wxz[RPT + 4];          // szz rows r0 - 1 .. r0 + RPT + 1 ; sxz rows r0 - 2 .. r0 + RPT
+            auto zoff = [&](int k) { return ((k < 2 ? max(r0 + k - 1, 0) : k >= RPT + 1 ? min(r0 + k - 1, ER - 1) : r0 + k - 1) - r0) * EW; };
+            auto xoff = [&](int k) { return ((k < 2 ? max(r0 + k - 2, 0) : k >= RPT + 1 ? min(r0 + k - 2, ER - 1) : r0 + k - 2) - r0) * EW; };
 #pragma unroll
-            for (int k = 0; k < RPT + 3; k++) {
-                int oz = (k - 1) * EW, ox = (k - 2) * EW;
-                if (k < 2) { oz = (max(r0 + k - 1, 0) - r0) * EW; ox = (max(r0 + k - 2, 0) - r0) * EW; }
-                if (k >= RPT + 1) { oz = (min(r0 + k - 1, ER - 1) - r0) * EW; ox = (min(r0 + k - 2, ER - 1) - r0) * EW; }
-                wzz[k] = ZZ[oz]; wxz[k] = XZ[ox];
-            }
+            for (int k = 0; k < 4; k++) { wzz[k] = ZZ[zoff(k)]; wxz[k] = XZ[xoff(k)]; }
 #pragma unroll
             for (int j = 0; j < RPT; j++) {
+                if (j + 1 < RPT) { wzz[j + 4] = ZZ[zoff(j + 4)]; wxz[j + 4] = XZ[xoff(j + 4)]; }
                 if (!((vmask >> j) & 1u)) continue;
                 const float *xzr = XZ + j * EW, *xxr = XX + j * EW;
                 float dszz_dz = c1z * (wzz[j + 2] - wzz[j + 1]) - c2z * (wzz[j + 3] - wzz[j]);

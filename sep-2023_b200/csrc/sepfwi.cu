@@ -783,9 +783,14 @@ static ResPlan resident_plan(const sepfwi_handle *h, int nb)
         if (!ok) continue;
         const int per = std::min(nb, h->nSM / ctas);
         const int launches = (nb + per - 1) / per;
-        const double c = launches * (1.5 + 0.25 * rpt);     // us per time step: exchange latency + per-row work
+        // measured us per time step of one launch (B200): exchange + barriers ~1.2, ~0.6 per row of a thread, more once the
+        // coefficient registers spill (rpt > 11)
+        const double c = launches * (1.2 + 0.6 * rpt + (rpt > 11 ? 2.0 * (rpt - 11) : 0.0));
         if (c < bestc) { bestc = c; best.rpt = rpt; best.ntx = ntx; best.ntz = ntz; best.orows = OR; best.per_launch = per; }
     }
+    // the launch-per-step streaming kernels: latency-bound below ~10 us per step, ~7e10 cell-updates/s once a batch fills the SMs
+    const double t_stream = std::max(10.0, 1e6 * (double)nb * d.nzA * d.nx / 7.0e10);
+    if (best.rpt && !forced && bestc >= t_stream) best = ResPlan();
     if (getenv("SEPFWI_PLAN_DEBUG")) fprintf(stderr, "resident_plan: nb %d -> rpt %d, %d x %d tiles of %d x %d, %d shots per launch\n", nb, best.rpt, best.ntx, best.ntz, best.orows, RS_OW, best.per_launch);
     return best;
 }
