@@ -4,6 +4,7 @@
     FWI(Vp, Vs, Den, Stf, opt, Mask, Vp_bounds, Vs_bounds, Den_bounds)           (:66-127)
     FWI_obscalc(Vp, Vs, Den, Stf, para_fname)                                    (:131-141)
     FWI_Lame_Den / FWI_IP_IS_Den / FWI_Vp_Vs_IP / FWI_Vp_Vs_IS                   (:146-395)
+    FWI_Rock_Physics_VRH / FWI_Rock_Physics_gassmann (PHI, CC, SW)               (:401-619)
 
 Every parameterisation is the same module -- pad three (nz_orig, nx_orig) fields to the padded grid, blend
 with the frozen reference model through `Mask`, map to (Lambda [MPa], Mu [MPa], Den) and call the op -- so it
@@ -136,6 +137,63 @@ class FWI_Vp_Vs_IS(_ThreeParameterFWI):
     def to_lame(vp, vs, is_):
         den = is_ / vs
         return den * vp ** 2 - 2.0 * is_ * vs, is_ * vs, den
+
+
+# Mineral / fluid constants of the reference's rock-physics maps (FWI_ops.py:459-471, 575-587): quartz, clay, water,
+# hydrocarbon bulk moduli [Pa], quartz / clay shear moduli [Pa], densities [kg/m^3], consolidation parameter.
+ROCK = dict(k_q=37.00e9, k_c=21.00e9, k_w=2.25e9, k_h=0.04e9, mu_q=44.00e9, mu_c=10.00e9,
+            rho_q=2.65e3, rho_c=2.55e3, rho_w=1.00e3, rho_h=0.10e3, cs=20.0)
+
+
+def _density(phi, cc, sw):
+    """Volume average of fluid (water / hydrocarbon) and skeleton (clay / quartz) densities."""
+    R = ROCK
+    rho_f = R['rho_w'] * sw + R['rho_h'] * (1 - sw)
+    rho_s = R['rho_c'] * cc + R['rho_q'] * (1 - cc)
+    return rho_f * phi + rho_s * (1 - phi)
+
+
+class FWI_Rock_Physics_VRH(_ThreeParameterFWI):
+    """Porosity, clay content, water saturation -> Voigt-Reuss-Hill average moduli (FWI_ops.py:451-507):
+    bulk modulus = mean of the Voigt (arithmetic) and Reuss (harmonic) averages over the four constituents,
+    shear modulus = half the Voigt average of the solid part (the Reuss shear modulus of a fluid-bearing mix is 0)."""
+    NAMES = ("PHI", "CC", "SW")
+
+    def __init__(self, PHI, CC, SW, Stf, opt, Mask=None, PHI_bounds=None, CC_bounds=None, SW_bounds=None):
+        super().__init__(PHI, CC, SW, Stf, opt, Mask, PHI_bounds, CC_bounds, SW_bounds)
+
+    @staticmethod
+    def to_lame(phi, cc, sw):
+        R = ROCK
+        k_voigt = (1 - phi) * (R['k_c'] * cc + R['k_q'] * (1 - cc)) + phi * (R['k_w'] * sw + R['k_h'] * (1 - sw))
+        k_reuss = 1 / ((1 - phi) * (cc / R['k_c'] + (1 - cc) / R['k_q']) + phi * (sw / R['k_w'] + (1 - sw) / R['k_h']))
+        k = 0.5 * (k_voigt + k_reuss)
+        mu = 0.5 * ((1 - phi) * (R['mu_c'] * cc + R['mu_q'] * (1 - cc)) + 0)
+        return (k - 2. / 3. * mu) / 1e6, mu / 1e6, _density(phi, cc, sw)
+
+
+class FWI_Rock_Physics_gassmann(_ThreeParameterFWI):
+    """Porosity, clay content, water saturation -> Gassmann fluid substitution on a consolidation-parameter dry frame
+    (FWI_ops.py:567-619, after PyFWI).  The P modulus uses 0.75 mu_d exactly as the reference does (:606)."""
+    NAMES = ("PHI", "CC", "SW")
+
+    def __init__(self, PHI, CC, SW, Stf, opt, Mask=None, PHI_bounds=None, CC_bounds=None, SW_bounds=None):
+        super().__init__(PHI, CC, SW, Stf, opt, Mask, PHI_bounds, CC_bounds, SW_bounds)
+
+    @staticmethod
+    def to_lame(phi, cc, sw):
+        R = ROCK
+        k_f = R['k_w'] * sw + R['k_h'] * (1 - sw)
+        k_s = R['k_c'] * cc + R['k_q'] * (1 - cc)
+        mu_s = R['mu_c'] * cc + R['mu_q'] * (1 - cc)
+        k_d = k_s * ((1 - phi) / (1 + R['cs'] * phi))
+        mu_d = mu_s * ((1 - phi) / (1 + 1.5 * R['cs'] * phi))
+        delta = ((1 - phi) / phi) * (k_f / k_s) * (1 - (k_d / (k_s - k_s * phi)))
+        k_u = (phi * k_d + (1 - (1 + phi) * (k_d / k_s)) * k_f) / (phi * (1 + delta))
+        rho = _density(phi, cc, sw)
+        vp = torch.sqrt((k_u + 0.75 * mu_d) / rho)
+        vs = torch.sqrt(mu_d / rho)
+        return rho * (vp ** 2 - 2 * vs ** 2) / 1e6, rho * vs ** 2 / 1e6, rho
 
 
 class FWI_obscalc(nn.Module):

@@ -157,3 +157,36 @@ def test_reference_notebook_lbfgs_iterate0(tmp_path):
     # cannot be pinned to 6 digits, only bracketed by the two deterministic gradients
     assert min(abs(res[True][1] - 2.14289), abs(res[False][1] - 2.14289)) <= 0.02 * 2.14289
     fwi_ops.clear_cache()
+
+
+def test_lbfgs_driver_follows_the_reference_notebook_trace(tmp_path):
+    """PyTorchObjective + scipy L-BFGS-B with the reference's options on the reference's own experiment 001
+    (sepfwi.drivers mirrors Main-001-FWI-Anomaly-Vp-Vs-Den.py).  The notebook logs
+        iterate 0  f = 1.51116D+04,  iterate 1  f = 1.13748D+04,  iterate 2  f = 3.05521D+03,  iterate 3  f = 2.11215D+03
+    The first line search only depends on f and g at x0, so iterates 1-2 test the whole gradient (all three parameter
+    classes through the autograd chain), not just its max-norm.  The reference's gradient carries its residual-injection
+    race (see test_reference_notebook_lbfgs_iterate0), so the trace is followed with ref_race_compat on and only to the
+    accuracy the race's hardware dependence allows; the race-free path must decrease the misfit at least as fast."""
+    from sepfwi import drivers, fwi_ops
+    prob = drivers.anomaly_problem("001")
+    notebook = [1.51116e4, 1.13748e4, 3.05521e3, 2.11215e3]
+    traces = {}
+    for compat in (True, False):
+        files = drivers.write_files(prob, str(tmp_path / ("c%d" % compat)), ref_race_compat=compat or None)
+        drivers.generate_data(prob, files)
+        fwi, obj, log = drivers.invert(prob, files, nIter=3)
+        traces[compat] = [f for _, f, _, _ in log]
+        assert obj.nfev <= 8 and len(log) == 4
+        assert fwi.Vp.grad is not None and fwi.Vp.grad.shape == (prob.nz, prob.nx)
+    msg = "L-BFGS f trace: notebook %s | race-compat %s | race-free %s" % (
+        ["%.5e" % v for v in notebook], ["%.5e" % v for v in traces[True]], ["%.5e" % v for v in traces[False]])
+    print(msg)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        open(os.path.join(out, "notebook_lbfgs_trace.txt"), "w").write(msg + "\n")
+    assert abs(traces[True][0] - notebook[0]) <= 2e-5 * notebook[0]
+    assert abs(traces[True][1] - notebook[1]) <= 0.02 * notebook[1]          # first step: direction = -g(x0)
+    for tr in traces.values():
+        assert tr[1] < tr[0] and tr[2] < 0.5 * tr[1] and tr[3] < tr[2]       # same order of decrease as the notebook
+        assert tr[3] < 0.2 * tr[0]
+    fwi_ops.clear_cache()

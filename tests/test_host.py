@@ -167,3 +167,56 @@ def test_fwi_module_parameterisations_map_to_lame():
     l4, m4, d4 = F.FWI_Vp_Vs_IS.to_lame(vp, vs, vs * den)
     assert d4.item() == pytest.approx(2200.0) and l4.item() == pytest.approx(l3.item(), rel=1e-6) and m4.item() == pytest.approx(m3.item(), rel=1e-6)
     assert F.FWI_Lame_Den.to_lame(lam, mu, den) == (lam, mu, den)
+
+
+def test_rock_physics_maps_match_reference_golden(golden_dir):
+    """(PHI, CC, SW) -> (Lambda, Mu, Den) of FWI_Rock_Physics_VRH / _gassmann against vectors produced by executing the
+    reference's own statements (tests/golden/make_rockphys_golden.py; FWI_ops.py:451-507, 567-619).  fp32 on both sides."""
+    import torch
+    from sepfwi import FWI_ops as F
+    g = np.load(os.path.join(golden_dir, "rockphys.npz"))
+    phi, cc, sw = (torch.from_numpy(g[k]) for k in ("PHI", "CC", "SW"))
+    for key, cls in (("vrh", F.FWI_Rock_Physics_VRH), ("gassmann", F.FWI_Rock_Physics_gassmann)):
+        lam, mu, den = cls.to_lame(phi, cc, sw)
+        for name, mine in (("Lambda", lam), ("Mu", mu), ("Den", den)):
+            ref = g["%s_%s" % (key, name)]
+            scale = np.abs(ref).max()
+            assert np.abs(mine.numpy() - ref).max() <= 2e-6 * scale, (key, name)
+
+
+class _ToyFWI(object):
+    pass
+
+
+def test_pytorch_objective_drives_scipy_lbfgs():
+    """PyTorchObjective (Ops/FWI/obj_wrapper.py:10-97 interface): x0 / bounds packing, one evaluation per new x,
+    gradients handed to scipy's L-BFGS-B exactly as the reference drivers do (Main-001-...py:157-168)."""
+    import torch
+    from scipy import optimize
+    from sepfwi.obj_wrapper import PyTorchObjective
+
+    class Quad(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.A = torch.nn.Parameter(torch.zeros(3, 4))
+            self.B = torch.nn.Parameter(torch.ones(5))
+            self.register_buffer("A_ref", torch.zeros(3, 4))
+            self.Bounds = {"B": (np.full(5, 0.5), np.full(5, 4.0))}
+
+        def forward(self):
+            ta = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+            return ((self.A - ta) ** 2).sum() + ((self.B - 0.25) ** 2).sum()
+
+    m = Quad()
+    obj = PyTorchObjective(m, lambda: m())
+    assert obj.x0.dtype == np.float64 and obj.x0.size == 17 and list(obj.param_shapes) == ["A", "B"]
+    assert obj.bounds.lb[:12].max() == -np.inf and np.all(obj.bounds.lb[12:] == 0.5) and np.all(obj.bounds.ub[12:] == 4.0)
+    f0 = obj.fun(obj.x0)
+    g0 = obj.jac(obj.x0)
+    assert obj.nfev == 1                                     # fun + jac of the same x: one evaluation
+    assert f0 == pytest.approx(sum(k * k for k in range(12)) + 5 * 0.75 ** 2)
+    assert np.allclose(g0[:12], -2.0 * np.arange(12)) and np.allclose(g0[12:], 1.5)
+    r = optimize.minimize(obj.fun, obj.x0, method="L-BFGS-B", jac=obj.jac, bounds=obj.bounds,
+                          options={"maxiter": 50, "maxcor": 5, "ftol": 1e-14, "gtol": 1e-10})
+    assert np.allclose(r.x[:12], np.arange(12), atol=1e-4) and np.allclose(r.x[12:], 0.5)    # B sits on its lower bound
+    assert np.allclose(m.B.detach().numpy(), obj.unpack_parameters(obj.cached_x)["B"].numpy())
