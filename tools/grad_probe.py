@@ -1,4 +1,4 @@
-"""Gradient-loop timing probe: python tools/t2.py workload nsteps batch  (env SEPFWI_LZ / SEPFWI_LZE / SEPFWI_FORCE)"""
+"""Gradient-loop timing probe: python tools/grad_probe.py workload nsteps batch  (env SEPFWI_LZ / SEPFWI_LZE / SEPFWI_FORCE)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "sep-2023_b200"), os.path.join(ROOT, "tests")]
