@@ -80,7 +80,7 @@ def _shots(para, shot_ids, Stf):
     stf = Stf.detach().cpu().numpy() if isinstance(Stf, torch.Tensor) else np.asarray(Stf)
     stf = np.ascontiguousarray(stf, np.float32)
     sv = fwi_utils.load_survey(para["survey_fname"], shot_ids, para["nPoints_pml"])
-    return [ShotSpec(s["zs"], s["xs"], s["zrec"], s["xrec"], stf[int(sid)], s["src_rxz"])
+    return [ShotSpec(s["zs"], s["xs"], s["zrec"], s["xrec"], stf[int(sid)], s["src_rxz"], weights=s.get("weights"))
             for s, sid in zip(sv, shot_ids)], stf.shape
 
 

@@ -52,8 +52,11 @@ def paraGen(nz, nx, dz, dx, nSteps, dt, f0, nPml, nPad, para_fname, survey_fname
 
 
 def surveyGen(z_src, x_src, z_rec, x_rec, survey_fname, Windows=None, Weights=None, Src_Weights=None,
-              Src_rxz=None, Rec_rxz=None):
-    """Write survey_file.json; every shot shares the receiver line (interior grid indices)."""
+              Src_rxz=None, Rec_rxz=None, Das_sensitivity=None):
+    """Write survey_file.json; every shot shares the receiver line (interior grid indices).
+    `Das_sensitivity` (extension): (nrec, 3) weights of (exx, ezz, exz) per channel -- an arbitrarily oriented
+    fiber as in DAS_Waveform_Modeling/src/elasticSolver.py:270-276 instead of the reference op's straight horizontal /
+    vertical fiber (libCUFD.cu:327-332); recorded as ett and injected by the adjoint with the same weights."""
     z_src, x_src = np.asarray(z_src).tolist(), np.asarray(x_src).tolist()
     z_rec, x_rec = np.asarray(z_rec).tolist(), np.asarray(x_rec).tolist()
     survey = {'nShots': len(x_src)}
@@ -70,6 +73,9 @@ def surveyGen(z_src, x_src, z_rec, x_rec, survey_fname, Windows=None, Weights=No
             shot['src_rxz'] = Src_rxz[i]
         if Rec_rxz is not None:
             shot['rec_rxz'] = np.asarray(Rec_rxz).tolist()
+        if Das_sensitivity is not None:
+            w = np.asarray(Das_sensitivity, np.float64).reshape(len(x_rec), 3)
+            shot['das_sensitivity'] = w.tolist()
         survey['shot' + str(i)] = shot
     with open(survey_fname, 'w') as fp:
         json.dump(survey, fp)
@@ -108,7 +114,7 @@ def read_json_first_line(fname):
 
 def load_survey(survey_fname, shot_ids, nPml):
     """Parse survey_file.json for `shot_ids` the way Src_Rec does (Src/Src_Rec.cu:74-120):
-    +nPml on every index.  Returns a list of dict(zs, xs, zrec, xrec, src_rxz)."""
+    +nPml on every index.  Returns a list of dict(zs, xs, zrec, xrec, src_rxz, weights)."""
     js = read_json_first_line(survey_fname)
     out = []
     for sid in shot_ids:
@@ -117,5 +123,7 @@ def load_survey(survey_fname, shot_ids, nPml):
         out.append(dict(zs=int(s['z_src']) + nPml, xs=int(s['x_src']) + nPml,
                         zrec=np.asarray(s['z_rec'][:n], np.int32) + nPml,
                         xrec=np.asarray(s['x_rec'][:n], np.int32) + nPml,
-                        src_rxz=float(s.get('src_rxz', 1.0))))
+                        src_rxz=float(s.get('src_rxz', 1.0)),
+                        weights=(np.asarray(s['das_sensitivity'], np.float32).reshape(n, 3)
+                                 if 'das_sensitivity' in s else None)))
     return out
