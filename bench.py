@@ -59,6 +59,14 @@ def workload(name):
         src = [(2, 4000)]
         zrec, xrec = np.full(7980, 2), np.arange(10, 7990)
         desc = "C5-size 8000x2000 (padded 2080x8064) sample, nt=120"
+    elif name == "ref":
+        # the reference's own experiment grid (notebooks/Main-001-...py:28-72): 101 x 201, 181 adjacent receivers at z = 95
+        nz, nx, nt, f0 = 101, 201, 1501, 10.0
+        vp = np.full((nz, nx), 4000.0)
+        vp[42:58, 42:58] += 80.0
+        src = [(1, 100)]
+        zrec, xrec = np.full(181, 95), np.arange(10, 191)
+        desc = "reference experiment 101x201 (padded 192x265), nt=1501, fiber z=95"
     else:
         raise SystemExit("unknown workload %s" % name)
     nPml = 32
@@ -66,8 +74,9 @@ def workload(name):
     vp_pad = problems.pad_model(vp, nPml, nPad)
     true = problems.lame_from_vp(vp_pad)
     start = problems.lame_from_vp(problems.pad_model(problems.smooth(vp, 10) if name != "c5s" else vp * 0.98, nPml, nPad))
-    return dict(name=name, desc=desc, nz=NZ, nx=NX, nPml=nPml, nPad=nPad, nSteps=nt, dz=10.0, dx=10.0, dt=1.0e-3, f0=f0,
-                true=true, start=start, src=src, zrec=zrec, xrec=xrec, stf=problems.ricker(f0, nt, 1.0e-3),
+    h, dt = (20.0, 2.0e-3) if name == "ref" else (10.0, 1.0e-3)
+    return dict(name=name, desc=desc, nz=NZ, nx=NX, nPml=nPml, nPad=nPad, nSteps=nt, dz=h, dx=h, dt=dt, f0=f0,
+                true=true, start=start, src=src, zrec=zrec, xrec=xrec, stf=problems.ricker(f0, nt, dt),
                 live=(NZ - nPad) * NX, interior=nz * nx)
 
 

@@ -788,8 +788,11 @@ static ResPlan resident_plan(const sepfwi_handle *h, int nb)
         const double c = launches * (1.2 + 0.6 * rpt + (rpt > 11 ? 2.0 * (rpt - 11) : 0.0));
         if (c < bestc) { bestc = c; best.rpt = rpt; best.ntx = ntx; best.ntz = ntz; best.orows = OR; best.per_launch = per; }
     }
-    // the launch-per-step streaming kernels: latency-bound below ~10 us per step, ~7e10 cell-updates/s once a batch fills the SMs
-    const double t_stream = std::max(10.0, 1e6 * (double)nb * d.nzA * d.nx / 7.0e10);
+    // the launch-per-step streaming kernels (measured): latency floor 10 us per step, up to 30 us when the grid is mostly CPML
+    // (the edge warps' longer rows), ~7e10 interior and ~2.5e10 CPML cell-updates/s once a batch fills the SMs
+    const double cells = (double)d.nzA * d.nx;
+    const double inner = (double)std::max(0, d.nzA - 2 * (d.nPml + 5)) * std::max(0, d.nx - 2 * (d.nPml + 5));
+    const double t_stream = std::max(10.0 + 20.0 * (cells - inner) / cells, 1e6 * nb * (inner / 7.0e10 + (cells - inner) / 2.5e10));
     if (best.rpt && !forced && bestc >= t_stream) best = ResPlan();
     if (getenv("SEPFWI_PLAN_DEBUG")) fprintf(stderr, "resident_plan: nb %d -> rpt %d, %d x %d tiles of %d x %d, %d shots per launch\n", nb, best.rpt, best.ntx, best.ntz, best.orows, RS_OW, best.per_launch);
     return best;
