@@ -347,6 +347,10 @@ def main():
             line["large"] = extra_large(args, Propagator, ShotSpec, torch, dev, local, peak)
         except Exception as e:
             line["large"] = {"error": str(e)[:200]}
+        try:
+            line["reference_experiment"] = extra_reference_experiment(Propagator, ShotSpec, torch, dev, local, timed)
+        except Exception as e:
+            line["reference_experiment"] = {"error": str(e)[:200]}
     else:
         P.close()
 
@@ -420,6 +424,26 @@ def extra_fwi(args, Propagator, ShotSpec, torch, dev, local, world, rank, timed,
                 "s_per_evaluation": t, "forward_loop_ms": f_ms, "backward_loop_ms": b_ms,
                 "allreduce_ms": ar["ev"][0].elapsed_time(ar["ev"][1]) if world > 1 else 0.0,
                 "allreduce_bytes": int(4 * (3 * w["nz"] * w["nx"] + B * world * w["nSteps"] + 1))}
+
+
+def extra_reference_experiment(Propagator, ShotSpec, torch, dev, local, timed):
+    """One misfit + gradient evaluation of the reference's own experiment (notebooks/Main-001-...py: 101 x 201 grid padded to
+    192 x 265, nt = 1501, 19 shots, 181 adjacent receivers) -- what one L-BFGS function evaluation costs per GPU."""
+    w = workload("ref")
+    P0 = w["nPml"]
+    xs = np.arange(10, 191, 10)
+    shots = [ShotSpec(1 + P0, int(x) + P0, w["zrec"] + P0, w["xrec"] + P0, w["stf"]) for x in xs]
+    with Propagator(w["nz"], w["nx"], w["nPml"], w["nPad"], w["nSteps"], w["dz"], w["dx"], w["dt"], w["f0"],
+                    max_batch=len(shots), max_nrec=len(w["xrec"]), with_adjoint=True, device=local) as P:
+        P.set_model(*[torch.from_numpy(a).to(dev) for a in w["true"]])
+        obs = [o["ett"] for o in P.forward(shots, comps=("ett",), device_out=True)]
+        P.set_model(*[torch.from_numpy(a).to(dev) for a in w["start"]])
+        fn = lambda: P.gradient(shots, obs, device=True)
+        fn()
+        t = timed(fn, 2) / 2
+        f_ms, b_ms = P.last_timing()
+        return {"workload": w["desc"] + ", 19 shots in one batch", "s_per_evaluation": t, "shot_gradients_per_s": len(shots) / t,
+                "forward_loop_ms": f_ms, "backward_loop_ms": b_ms, "resident_forward_launches": P.resident_launches}
 
 
 def extra_large(args, Propagator, ShotSpec, torch, dev, local, peak):
