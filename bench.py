@@ -196,6 +196,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # the contract is ONE JSON line on stdout: whatever libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -365,9 +369,13 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
                                 "sample": "2 x %d of %d forward time steps of the same workload, CPU oracle port (C, OpenMP over rows), %.1f s"
                                           % (nt_sample - 1, w["nSteps"] - 1, dt)}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
