@@ -10,6 +10,7 @@
  *                                                               Boundary.cu:5-43 (done once, not per call)
  *   sepfwi_set_model <- Model constructor + host transposes     Model.cu:15-93, libCUFD.cu:67-77
  *   sepfwi_forward   <- cufd(calc_id = 2) shot loop             libCUFD.cu:170-347
+ *   sepfwi_forward_snapshots <- elasticSolver.forward_it(isrc, True)   DAS_Waveform_Modeling/src/elasticSolver.py:185-305
  *   sepfwi_gradient  <- cufd(calc_id = 0 / 1) shot loop         libCUFD.cu:170-724, 775-780
  *   sepfwi_ring_*    <- Bnd::field_from_bnd / field_to_bnd      Boundary.cu:55-101, utilities.cu:362-425
  *
@@ -108,6 +109,13 @@ int sepfwi_courant(sepfwi_handle *h, float *courant);
 
 /* Forward modelling of `nshots` shots (any number; processed max_batch at a time). */
 int sepfwi_forward(sepfwi_handle *h, int nshots, const sepfwi_shot *shots, int mem, void *stream);
+
+/* Sponge flavour only: forward modelling of ONE shot that also stores the interior (without the ndamp sponge cells) of
+ * sxx, szz, vx, vz after every time step `it` with it % save_step == 0 -- elasticSolver.forward_it(isrc, save_wavefield=True),
+ * DAS_Waveform_Modeling/src/elasticSolver.py:231-237,279-284,298-303.
+ *   snap : [(nSteps-1)/save_step + 1][4][nz - 2 nPml][nx - 2 nPml] floats in space `mem`, field order sxx, szz, vx, vz, each
+ *          image row-major [z][x] (the reference stores [x][z]; the Python layer transposes). */
+int sepfwi_forward_snapshots(sepfwi_handle *h, const sepfwi_shot *shot, int save_step, float *snap, int mem, void *stream);
 
 /* Misfit (+ gradient when with_adj) of `nshots` shots.
  *   misfit : HOST float, 0.5 * sum over shots and samples of (obs-syn)^2      (libCUFD.cu:427,776)

@@ -81,6 +81,9 @@ struct sepfwi_handle {
     size_t ro_flags = 0, ro_err = 0, ro_tptr = 0, ro_trec = 0, ro_rptr = 0, res_n = 0;
     int *res_errh = nullptr;                        // pinned copy of the error flag
     int res_used = 0;                               // launches of the resident kernel since creation (introspection)
+    // wavefield snapshots of the sponge flavour (sepfwi_forward_snapshots): destination, stride in time steps, pointer space
+    float *snap_dst = nullptr;
+    int snap_step = 0, snap_mem = SEPFWI_MEM_HOST;
     // host copies
     std::vector<float> hcz, hcx;
     float courant = 0.f;
@@ -958,11 +961,22 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
             if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, it + 1, mask, h->p.fiber, 0)));
         }
     } else {
+        const int nzI = d.nzA - 2 * d.nPml, nxI = d.nx - 2 * d.nPml;
         for (int it = 0; it < d.nSteps; it++) {
             const bool pr = it < h->prof_steps;
             LAUNCH(h, SEPFWI_K_VELOCITY_FWD, pr, st, (k_velocity_fwd<true><<<grd, blk, 0, st>>>(a)));
             LAUNCH(h, SEPFWI_K_STRESS_FWD, pr, st, (k_stress_fwd<true><<<grd, blk, 0, st>>>(a, it)));
             if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<true><<<rgrd, 128, 0, st>>>(a, it, mask, h->p.fiber, 0)));
+            if (h->snap_dst && it % h->snap_step == 0) {
+                // interior of sxx, szz, vx, vz of slot 0 after step `it` (elasticSolver.py:279-284)
+                static const int fld[4] = {F_SXX, F_SZZ, F_VX, F_VZ};
+                float *dst = h->snap_dst + (size_t)(it / h->snap_step) * 4 * nzI * nxI;
+                for (int f = 0; f < 4; f++)
+                    CU(cudaMemcpy2DAsync(dst + (size_t)f * nzI * nxI, (size_t)nxI * sizeof(float),
+                                         h->state + (size_t)(S_FWD + fld[f]) * d.fsz + (size_t)d.nPml * d.ldx + d.nPml, (size_t)d.ldx * sizeof(float),
+                                         (size_t)nxI * sizeof(float), nzI,
+                                         h->snap_mem == SEPFWI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+            }
         }
     }
     CU(cudaEventRecord(h->ev[1], st));
@@ -1007,6 +1021,16 @@ extern "C" int sepfwi_forward(sepfwi_handle *h, int nshots, const sepfwi_shot *s
         h->fwd_ms += ms;
     }
     return 0;
+}
+
+extern "C" int sepfwi_forward_snapshots(sepfwi_handle *h, const sepfwi_shot *shot, int save_step, float *snap, int mem, void *stream)
+{
+    if (!h || !shot || !snap || save_step < 1) return fail(SEPFWI_EINVAL, "bad argument");
+    if (!h->sponge) return fail(SEPFWI_EINVAL, "wavefield snapshots belong to the sponge flavour (elasticSolver.forward(save_wavefield=True))");
+    h->snap_dst = snap; h->snap_step = save_step; h->snap_mem = mem;
+    const int rc = sepfwi_forward(h, 1, shot, mem, stream);
+    h->snap_dst = nullptr;
+    return rc;
 }
 
 // Backward time loop of one batch, libCUFD.cu:500-653.

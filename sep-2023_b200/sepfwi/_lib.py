@@ -37,7 +37,7 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_courant", "sepfwi_forward", "sepfwi_gradient", "sepfwi_cufd", "sepfwi_cufd_clear_cache",
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
-           "sepfwi_kernel_name", "sepfwi_resident_launches"]
+           "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots"]
 NKERNEL = 16
 
 _lib = None
@@ -65,6 +65,7 @@ def lib():
         L.sepfwi_set_model.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sepfwi_courant.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.sepfwi_forward.argtypes = [C.c_void_p, C.c_int, C.POINTER(Shot), C.c_int, C.c_void_p]
+        L.sepfwi_forward_snapshots.argtypes = [C.c_void_p, C.POINTER(Shot), C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.sepfwi_gradient.argtypes = [C.c_void_p, C.c_int, C.POINTER(Shot), C.c_int, C.POINTER(C.c_float),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sepfwi_cufd.argtypes = [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_char_p]

@@ -80,11 +80,19 @@ class elasticSolver(object):
 
     def forward(self, save_wavefield=False):
         if save_wavefield:
-            raise NotImplementedError("wavefield snapshots are not exported by the GPU solver yet")
+            return [self.forward_it(i, True) for i in range(self.src_num)]
         outs = self._prop.forward([self._shot(i) for i in range(self.src_num)], comps=self._COMPS)
         return [self._solu(o) for o in outs]
 
     def forward_it(self, isrc, save_wavefield=False):
-        if save_wavefield:
-            raise NotImplementedError("wavefield snapshots are not exported by the GPU solver yet")
-        return self._solu(self._prop.forward([self._shot(isrc)], comps=self._COMPS)[0])
+        if not save_wavefield:
+            return self._solu(self._prop.forward([self._shot(isrc)], comps=self._COMPS)[0])
+        # snapshots every save_step steps of the interior, as (save_num, nx, nz) arrays (elasticSolver.py:231-237,279-303)
+        out, snaps = self._prop.forward_snapshots(self._shot(isrc), self.save_step, comps=self._COMPS)
+        solu = self._solu(out)
+        save_num = self.nt // self.save_step + 1
+        for k, name in enumerate(("sxx_wavefield", "szz_wavefield", "vx_wavefield", "vz_wavefield")):
+            w = np.zeros((save_num,) + snaps.shape[2:][::-1], np.float64)
+            w[:snaps.shape[0]] = np.transpose(snaps[:, k], (0, 2, 1))
+            solu[name] = w
+        return solu

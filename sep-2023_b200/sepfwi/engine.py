@@ -215,6 +215,22 @@ class Propagator(object):
                                    self._stream()))
         return res
 
+    def forward_snapshots(self, shot, save_step, comps=("pr", "vx", "vz", "ett")):
+        """Sponge flavour: forward modelling of one shot plus the interior of sxx, szz, vx, vz after every time step that is a
+        multiple of `save_step` (elasticSolver.forward_it(isrc, True)).  Returns (traces dict, snapshots) with snapshots
+        shaped [(nSteps-1)//save_step + 1, 4, nz - 2 nPml, nx - 2 nPml], fields in the order sxx, szz, vx, vz."""
+        keep = []
+        arr = self._shot_array([shot], keep)
+        d = {}
+        for name in comps:
+            buf = np.empty((shot.nrec, self.nSteps), np.float32)
+            arr[0].out[_COMP[name]] = buf.ctypes.data
+            d[name] = buf
+        p = self.params
+        snaps = np.zeros(((self.nSteps - 1) // int(save_step) + 1, 4, p.nz - p.nPad - 2 * p.nPml, p.nx - 2 * p.nPml), np.float32)
+        check(lib().sepfwi_forward_snapshots(self._h, arr, int(save_step), snaps.ctypes.data, _lib.MEM_HOST, self._stream()))
+        return d, snaps
+
     def gradient(self, shots, obs, with_adj=True, device=False, want_syn=False):
         """Misfit and gradient of `shots` against observed DAS data `obs` (list of [nrec, nSteps]).
         device=True: obs are CUDA tensors and the gradients are returned as CUDA tensors.

@@ -54,19 +54,35 @@ def cases():
         das_coord=np.stack([np.arange(40.0, 600.0, 80.0), np.full(7, 200.0)], axis=1),
         geo_coord=np.array([[64.0, 500.0], [560.0, 20.0], [320.0, 30.0]]),
         das_sensitivity=np.tile(np.array([[1.0, 0.25, 0, 0, 0, 0.5]]), (7, 1)))
+    # small heterogeneous case stored WITH wavefield snapshots (forward_it(isrc, True): every save_step = 10 steps)
+    nx, nz = 50, 40
+    vp = 2200.0 + 900.0 * (np.arange(nz)[None, :] / nz) + 60.0 * rng.standard_normal((nx, nz))
+    out["numba_wavefield"] = dict(
+        nx=nx, nz=nz, ndamp=10, dx=10.0, dz=10.0, dt=1e-3, nt=95, f0=20.0,
+        vp=vp, vs=vp / 1.732, rho=310.0 * vp ** 0.25,
+        src_coord=np.array([[250.0, 120.0]]),
+        das_coord=np.array([[100.0, 100.0], [300.0, 250.0]]),
+        geo_coord=np.array([[400.0, 300.0]]),
+        das_sensitivity=np.array([[1.0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 1.0]]))
     return out
 
 
 def main():
     es = import_reference_solver()
+    only = sys.argv[1:]
     for name, kw in cases().items():
+        if only and name not in only:
+            continue
         solver = es.elasticSolver(**kw)
         nshot = kw["src_coord"].shape[0]
         store = {"in_" + k: np.asarray(v) for k, v in kw.items()}
         for isrc in range(nshot):
-            solu = solver.forward_it(isrc, False)
+            solu = solver.forward_it(isrc, name == "numba_wavefield")
             for k in ("vx", "vz", "pr", "ett", "exx", "ezz", "exz"):
                 store["out%d_%s" % (isrc, k)] = solu[k]
+            if name == "numba_wavefield":
+                for k in ("sxx_wavefield", "szz_wavefield", "vx_wavefield", "vz_wavefield"):
+                    store["out%d_%s" % (isrc, k)] = solu[k].astype(np.float32)
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **store)
         print("wrote", path, os.path.getsize(path), "bytes")

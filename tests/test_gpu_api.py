@@ -12,7 +12,7 @@ from util import rel_l2
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["numba_homog", "numba_hetero"])
+@pytest.mark.parametrize("name", ["numba_homog", "numba_hetero", "numba_wavefield"])
 def test_elastic_solver_matches_numba_reference(golden_dir, name):
     """north_star: DAS seismograms within 1e-4 relative L2 of the Numba CPU modelling, computing in fp32."""
     from sepfwi.elasticSolver import elasticSolver
@@ -29,6 +29,16 @@ def test_elastic_solver_matches_numba_reference(golden_dir, name):
             assert rel_l2(s[k], ref) < 1e-4, (name, isrc, k, rel_l2(s[k], ref))
     one = solver.forward_it(0, False)
     assert np.array_equal(one["ett"], sol[0]["ett"])
+    if name == "numba_wavefield":
+        # forward_it(isrc, save_wavefield=True): interior snapshots every save_step = 10 steps, (save_num, nx, nz) arrays
+        snap = solver.forward_it(0, True)
+        assert np.array_equal(snap["ett"], one["ett"])
+        for k in ("sxx_wavefield", "szz_wavefield", "vx_wavefield", "vz_wavefield"):
+            ref = g["out0_" + k]
+            assert snap[k].shape == ref.shape == (95 // 10 + 1, 50, 40) and snap[k].dtype == np.float64
+            assert np.abs(ref[-1]).max() > 0 and rel_l2(snap[k], ref) < 1e-4, (k, rel_l2(snap[k], ref))
+        both = solver.forward(save_wavefield=True)
+        assert np.array_equal(both[0]["vx_wavefield"], snap["vx_wavefield"])
     with pytest.raises(ValueError):
         solver.set_model(kw["vp"][:-1], kw["vs"][:-1], kw["rho"][:-1])
 
