@@ -268,3 +268,29 @@ def test_fwi_op_with_per_channel_das_sensitivity(tmp_path):
         ratio[tag] = float((out[2].double() * dmu.double()).sum()) / ((Jp - Jm) / 2.0)
     assert abs(ratio["stock"] - 1.0) < 0.2 and abs(ratio["oriented"] - ratio["stock"]) < 0.05, ratio
     fwi_ops.clear_cache()
+
+
+def test_one_process_per_gpu_nccl_matches_single_process(tmp_path):
+    """torchrun, one process per GPU, shots sharded like Torch_Fwi.cpp:59-80, ONE NCCL all-reduce of the packed
+    [gradients | gstf | misfit] buffer -- the L-BFGS trace of the reference's experiment 001 must be the single-process one."""
+    import re
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "main_fwi_anomaly.py")
+
+    def run(prefix, exp):
+        for extra in (["--generate_data"], ["--nIter", "2"]):
+            p = subprocess.run(prefix + [tool, "--problem", "001", "--exp_name", exp] + extra, capture_output=True, text=True, timeout=600)
+            assert p.returncode == 0, p.stderr[-2000:]
+        return [float(m) for m in re.findall(r"At iterate\s+\d+\s+f= ([0-9.E+-]+)", p.stdout)]
+
+    one = run([sys.executable], str(tmp_path / "one"))
+    two = run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29533"], str(tmp_path / "two"))
+    assert len(one) == 3 and len(two) == 3
+    # the sum over shots is associated differently (per-rank partial sums), so agreement is to rounding, not bit-exact
+    assert np.allclose(one, two, rtol=2e-5), (one, two)

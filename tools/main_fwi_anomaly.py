@@ -27,12 +27,38 @@ ap.add_argument('--ngpu', type=int, default=1)
 ap.add_argument('--ref_race_compat', action='store_true', help="reproduce the reference's lost seam update in the residual injection")
 args = ap.parse_args()
 
+# one process per GPU under torchrun: shots are sharded over the ranks inside fwi_ops (sepfwi.dist), gradients and misfit are
+# summed by one NCCL all-reduce, every rank then takes the identical L-BFGS step
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+device = None
+if world > 1:
+    import torch
+    import torch.distributed as td
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    td.init_process_group("nccl", device_id=device)
+
 prob = drivers.anomaly_problem(args.problem)
-files = drivers.write_files(prob, args.exp_name, ref_race_compat=args.ref_race_compat or None)
+if rank == 0:
+    files = drivers.write_files(prob, args.exp_name, ref_race_compat=args.ref_race_compat or None)
+if world > 1:
+    td.barrier()
+    files = dict(para=os.path.join(args.exp_name, "para_file.json"), survey=os.path.join(args.exp_name, "survey_file.json"),
+                 data=os.path.join(args.exp_name, "Data"))
 if args.generate_data:
-    drivers.generate_data(prob, files, ngpu=args.ngpu)
-    sys.exit('End of Data Generation')
-fwi, obj, log = drivers.invert(prob, files, nIter=args.nIter, ngpu=args.ngpu)
+    drivers.generate_data(prob, files, ngpu=args.ngpu, device=device)
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
+    if rank == 0:
+        print('End of Data Generation')
+    sys.exit(0)
+fwi, obj, log = drivers.invert(prob, files, nIter=args.nIter, ngpu=args.ngpu, device=device)
+if world > 1:
+    td.destroy_process_group()
+if rank != 0:
+    sys.exit(0)
 ref = NOTEBOOK_F[args.problem]
 for k, f, g, t in log:
     print("At iterate %4d    f= %.5E    |proj g|= %.5E    (%.2f s)%s" % (k, f, g, t, "    notebook f= %.5E" % ref[k] if k < len(ref) else ""))
