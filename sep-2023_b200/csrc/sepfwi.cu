@@ -68,6 +68,7 @@ struct sepfwi_handle {
     bool fused = false;    // tile kernels (kernels = 2); their backward half also serves kernels = 0 until the streaming one lands
     bool stream = false;   // register-streaming kernels (kernels = 0)
     int nSM = 148;
+    size_t smem_optin = 0; // largest opt-in dynamic shared memory per block on this device
     bool pdl = true;       // programmatic dependent launch inside the time loops (SEPFWI_PDL=0 disables)
     int4 *work[3] = {nullptr, nullptr, nullptr};   // work lists of the streaming kernels (device): forward, reconstruction, adjoint
     size_t work_cap[3] = {0, 0, 0};
@@ -358,6 +359,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
         h->nSM = prop.multiProcessorCount;
+        h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     }
     if (h->fused) {
         CU(cudaFuncSetAttribute(k_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
@@ -738,6 +740,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
 // ------------------------------------------------------------------------------------------
 // Shared-memory-resident forward loop (kernels_resident.cuh): tiling plan, tables, cooperative launch.
 struct ResPlan { int rpt = 0, ntx = 0, ntz = 0, orows = 0, per_launch = 0; };
+static const int RES_UNAVAILABLE = 12345;   // run_resident: the cooperative launch was refused; nothing has run
 static int resident_check(sepfwi_handle *h);
 
 template <int RPT>
@@ -777,7 +780,7 @@ static ResPlan resident_plan(const sepfwi_handle *h, int nb)
         const int ORmax = 8 * rpt - 8, ER = 8 * rpt, ntz = (d.nzA + ORmax - 1) / ORmax;
         const int OR = (d.nzA + ntz - 1) / ntz;      // equal tiles
         const int ctas = ntx * ntz;
-        if (ctas > h->nSM || OR < 4) continue;
+        if (ctas > h->nSM || OR < 4 || rs_smem_bytes(rpt) > h->smem_optin) continue;
         bool ok = true;
         for (int t = 0; t < ntz && ok; t++) {
             const int lo = std::max(t * OR - 4, 0), hi = std::min(t * OR - 4 + ER - 1, d.nzA - 1);
@@ -879,6 +882,8 @@ static int run_resident(sepfwi_handle *h, const ResPlan &pl, int s0, int n, int 
     ra.ringPtr = h->res_dev + h->ro_rptr; ra.ringEnt = h->res_ring;
     const dim3 grid(nT, n);
     cudaError_t e = cudaErrorInvalidValue;
+    if (getenv("SEPFWI_RES_FAKE_REFUSE")) e = cudaErrorCooperativeLaunchTooLarge;     // test hook for the fallback below
+    else
     switch (pl.rpt) {
     case 3: e = launch_resident<3>(grid, a, ra, st); break;
     case 4: e = launch_resident<4>(grid, a, ra, st); break;
@@ -892,7 +897,13 @@ static int run_resident(sepfwi_handle *h, const ResPlan &pl, int s0, int n, int 
     case 12: e = launch_resident<12>(grid, a, ra, st); break;
     case 13: e = launch_resident<13>(grid, a, ra, st); break;
     }
-    if (e != cudaSuccess) return fail(SEPFWI_ECUDA, "resident forward kernel (RPT %d, %d x %d tiles, %d shots): %s", pl.rpt, pl.ntx, pl.ntz, n, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        // the device cannot co-schedule the tiles (fewer SMs than planned for, a partitioned GPU, ...): not an error of the
+        // call -- the caller falls back to the launch-per-step streaming kernels and stops planning resident launches
+        cudaGetLastError();
+        fail(SEPFWI_ECUDA, "resident forward kernel (RPT %d, %d x %d tiles, %d shots): %s", pl.rpt, pl.ntx, pl.ntz, n, cudaGetErrorString(e));
+        return RES_UNAVAILABLE;
+    }
     CU(cudaMemcpyAsync(h->res_errh, h->res_dev + h->ro_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     h->res_used++;
     return 0;
@@ -918,15 +929,18 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
     dim3 blk(BX, BY), grd((d.nx + BX - 1) / BX, (d.nzA + BY - 1) / BY, nb);
     dim3 rgrd((mrec + 127) / 128, nb), ringgrd((d.ringLen + 255) / 256, nb);
     CU(cudaEventRecord(h->ev[0], st));
-    const ResPlan rpl = resident_plan(h, nb);
+    ResPlan rpl = resident_plan(h, nb);
     if (rpl.rpt) {
         // the whole time loop of `per_launch` shots per cooperative launch, tiles resident in shared memory
         for (int s0 = 0; s0 < nb; s0 += rpl.per_launch) {
             const bool pr = h->prof_steps > 0;
             int rc = 0;
             LAUNCH(h, SEPFWI_K_RESIDENT_FWD, pr, st, (rc = run_resident(h, rpl, s0, std::min(rpl.per_launch, nb - s0), mrec > 0 ? mask : 0, save_ring, st)));
-            if (rc) return rc;
+            if (rc == RES_UNAVAILABLE && s0 == 0) { h->resident = false; rpl = ResPlan(); break; }
+            if (rc) return rc == RES_UNAVAILABLE ? SEPFWI_ECUDA : rc;
         }
+    }
+    if (rpl.rpt) {
     } else if (h->stream) {
         StreamArgs sa;
         int rc = stream_plan(h, nb, 0, sa);

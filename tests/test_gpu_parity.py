@@ -397,3 +397,25 @@ def test_full_size_c5_grid_streaming_vs_baseline():
     twice, _ = _forward_full(w, 0, ShotSpec, Propagator, scale=2.0)
     for c in ("pr", "vx", "vz", "ett"):
         _assert_doubled(twice[c], stream[c], c)
+
+
+def test_resident_launch_refused_falls_back_to_streaming_kernels(monkeypatch):
+    """A device that cannot co-schedule the tiles (cooperative launch refused) must not fail the call: the launch-per-step
+    streaming kernels take over (another CUDA path, never a CPU path) and later calls stop planning resident launches."""
+    _, Propagator, ShotSpec = _mods()
+    prob = problems.small()
+    monkeypatch.setenv("SEPFWI_RES_FAKE_REFUSE", "1")
+    with make_prop(Propagator, prob, max_batch=3, kernels=0) as P:
+        P.set_model(*prob.true)
+        shots = cuda_shots(prob, ShotSpec)
+        a = P.forward(shots)
+        n_launch = P.launches
+        b = P.forward(shots)
+        assert P.resident_launches == 0 and P.launches - n_launch >= prob.nSteps - 1
+    monkeypatch.delenv("SEPFWI_RES_FAKE_REFUSE")
+    with make_prop(Propagator, prob, max_batch=3, kernels=3) as P:
+        P.set_model(*prob.true)
+        c = P.forward(shots)
+    for sid in range(prob.nshots):
+        for comp in ("pr", "vx", "vz", "ett"):
+            assert np.array_equal(a[sid][comp], c[sid][comp]) and np.array_equal(b[sid][comp], c[sid][comp])
