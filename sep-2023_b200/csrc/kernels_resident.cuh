@@ -34,7 +34,7 @@ struct ResArgs {
     int ntx, ntz, slot0;         // tiles; first slot of this launch (blockIdx.y = slot - slot0)
     int orows;                   // own rows of a tile, <= 8 RPT - 8
     int mask, fiber, save_ring;
-    int dbg;                     // timing experiments only (SEPFWI_RES_DEBUG): 1 no exchange, 2 no stress phase, 4 no velocity phase
+    int dbg;                     // timing experiments only (SEPFWI_RES_DEBUG): 1 no exchange wait, 2 no stress phase, 4 no velocity phase, 8 no fence + flag, 16 no v traces
     int *flags;                  // [gridDim.y][ntx*ntz][RS_FLAGW] inboxes: slot (dz+1)*3+(dx+1) = steps completed by the neighbour in direction
                                  //   (dz, dx); one 128-byte line per tile (no two tiles poll the same line); missing neighbours pre-set to INT_MAX
     int *err;                    // set to 1 when a neighbour never arrives (the launch then drains instead of hanging)
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(RS_NT, 1) k_resident_fwd(const KArgs a, const 
     int dead = 0;
     for (int it = 0; it <= nSteps - 2; it++) {
         // ================= stress phase: v(it) is read-only =================
-        if (ra.mask && it >= 1 && n1 > n0) rs_record_v<ER>(a, ra, F, s, n0, n1, trec, tz0, tx0, it);
+        if (ra.mask && it >= 1 && n1 > n0 && !(ra.dbg & 16)) rs_record_v<ER>(a, ra, F, s, n0, n1, trec, tz0, tx0, it);
         if (e1 > e0) rs_ring_save<ER>(a, ra, F, s, e0, e1, it, F_VZ, F_VX + 1);
         if (scol && !(ra.dbg & 2)) {
             const float *VZ = Fc + F_VZ * FS, *VX = Fc + F_VX * FS;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(RS_NT, 1) k_resident_fwd(const KArgs a, const 
         // ================= neighbour exchange of v(it+1) =================
         // producer: stores above -> barrier -> fence + release by one thread.  consumer: relaxed polls of the step counter
         // (no L1 invalidation), then L2 loads (ld.cg) issued after the poll's branch.
-        if (tid < 32) {
+        if (tid < 32 && !(ra.dbg & 8)) {
             __threadfence();
             if (outbox) rs_st_relaxed(outbox, it + 1);
         }
