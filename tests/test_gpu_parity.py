@@ -419,3 +419,45 @@ def test_resident_launch_refused_falls_back_to_streaming_kernels(monkeypatch):
     for sid in range(prob.nshots):
         for comp in ("pr", "vx", "vz", "ett"):
             assert np.array_equal(a[sid][comp], c[sid][comp]) and np.array_equal(b[sid][comp], c[sid][comp])
+
+
+@pytest.mark.parametrize("kernels", [0, 3])
+def test_ragged_and_empty_receiver_sets(kernels):
+    """Edge cases of the shot batch: shots with different receiver counts in one launch, a shot without any receiver, receivers
+    on the first / last recordable rows and columns, duplicate receivers on one cell, more shots than slots (several
+    batches) -- resident (0) and streaming (3) paths against the unfused baseline kernels, forward and gradient."""
+    _, Propagator, ShotSpec = _mods()
+    prob = problems.small()
+    P0 = prob.nPml
+    nzA, nx = prob.nz - prob.nPad, prob.nx
+    rng = np.random.default_rng(17)
+    stf = prob.stf[0]
+    full_z, full_x = prob.z_rec + P0, prob.x_rec + P0
+    shots = [
+        ShotSpec(prob.z_src[0] + P0, prob.x_src[0] + P0, full_z, full_x, stf),
+        ShotSpec(prob.z_src[1] + P0, prob.x_src[1] + P0, full_z[:7], full_x[:7], stf),
+        ShotSpec(prob.z_src[2] + P0, prob.x_src[2] + P0, np.zeros(0, np.int32), np.zeros(0, np.int32), stf),          # no receivers
+        ShotSpec(20 + P0, 30 + P0, np.array([1, nzA - 2, 40, 40, 40]), np.array([1, nx - 2, 60, 60, 61]), stf),        # grid rim, duplicates
+        ShotSpec(25 + P0, 70 + P0, rng.integers(P0, nzA - P0, 23), rng.integers(P0, nx - P0, 23), stf),
+    ]
+    res = {}
+    for kern in (kernels, 1):
+        with Propagator(prob.nz, prob.nx, prob.nPml, prob.nPad, prob.nSteps, prob.dz, prob.dx, prob.dt, prob.f0, max_batch=2,
+                        max_nrec=len(full_x), with_adjoint=True, device=0, kernels=kern) as P:
+            P.set_model(*prob.true)
+            fwd = P.forward(shots)
+            P.set_model(*prob.start)
+            obs = [f["ett"] for f in fwd]
+            g = P.gradient(shots, obs)
+            res[kern] = (fwd, g)
+    a, b = res[kernels], res[1]
+    for k, sh in enumerate(shots):
+        for c in ("pr", "vx", "vz", "ett"):
+            assert a[0][k][c].shape == (sh.nrec, prob.nSteps)
+            if sh.nrec:
+                assert rel_l2(a[0][k][c], b[0][k][c]) < 1e-5, (k, c)
+    assert np.array_equal(a[0][3]["ett"][2], a[0][3]["ett"][3])       # the two receivers on one cell record the same trace
+    assert abs(a[1]["misfit"] - b[1]["misfit"]) <= 1e-5 * abs(b[1]["misfit"])
+    for k in ("glam", "gmu", "grho"):
+        assert rel_l2(a[1][k], b[1][k]) < 1e-4, k
+    assert np.all(a[1]["gstf"][2] == b[1]["gstf"][2])
