@@ -24,7 +24,10 @@ namespace sepfwi {
 
 constexpr int RS_EW = 64;        // extended tile width (own 56 + 4-cell halo on each side)
 constexpr int RS_OW = 56;
-constexpr int RS_NG = 8;         // row groups
+#ifndef RS_NG_
+#define RS_NG_ 8
+#endif
+constexpr int RS_NG = RS_NG_;    // row groups (threads = 64 RS_NG)
 constexpr int RS_NT = RS_NG * RS_EW;
 constexpr int RS_PW = 32;        // rows / columns of CPML memory a tile can hold (>= nPml)
 constexpr int RS_SPIN_MAX = 1 << 22;
@@ -45,7 +48,7 @@ struct ResArgs {
 };
 
 __host__ __device__ constexpr size_t rs_smem_bytes(int RPT)
-{ return sizeof(float) * ((size_t)5 * 8 * RPT * RS_EW + 4 * RS_PW * RS_EW + (size_t)4 * 8 * RPT * RS_PW + 6 * 8 * RPT); }
+{ return sizeof(float) * ((size_t)5 * RS_NG * RPT * RS_EW + 4 * RS_PW * RS_EW + (size_t)4 * RS_NG * RPT * RS_PW + 6 * RS_NG * RPT); }
 
 __device__ __forceinline__ int rs_ld_acquire(const int *p)
 { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
@@ -116,7 +119,7 @@ __device__ __forceinline__ void rs_ring_save(const KArgs &a, const ResArgs &ra, 
 template <int RPT>
 __global__ void __launch_bounds__(RS_NT, 1) k_resident_fwd(const KArgs a, const ResArgs ra)
 {
-    constexpr int ER = 8 * RPT, EW = RS_EW, FS = ER * EW;
+    constexpr int ER = RS_NG * RPT, EW = RS_EW, FS = ER * EW;
     constexpr int NHALO = 8 * EW + 8 * (ER - 8);      // 4 rows above + 4 below, 4 + 4 columns beside the rows between
     constexpr int HPT = (NHALO + RS_NT - 1) / RS_NT;
     extern __shared__ __align__(16) float sm[];

@@ -777,7 +777,7 @@ static ResPlan resident_plan(const sepfwi_handle *h, int nb)
     double bestc = 1e300;
     for (int rpt : k_res_rpts) {
         if (forced && rpt != forced) continue;
-        const int ORmax = 8 * rpt - 8, ER = 8 * rpt, ntz = (d.nzA + ORmax - 1) / ORmax;
+        const int ORmax = RS_NG * rpt - 8, ER = RS_NG * rpt, ntz = (d.nzA + ORmax - 1) / ORmax;
         const int OR = (d.nzA + ntz - 1) / ntz;      // equal tiles
         const int ctas = ntx * ntz;
         if (ctas > h->nSM || OR < 4 || rs_smem_bytes(rpt) > h->smem_optin) continue;
