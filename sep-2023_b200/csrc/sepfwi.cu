@@ -702,7 +702,14 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
             const double it_i = 6 * ((Lz + 4 + 5) / 6) + 3.0, it_e = (le + 4 + 3.0) * edge_cost;   // rows per item (+3: prologue)
             const double work = (n_in * it_i + n_ed * it_e) * nb / conc, longest = std::max(it_i, (le + 4 + 3.0) * edge_latc);
             // one wave or less: the longest item is the time; many waves: throughput plus half an item of tail
-            const double c = std::max(longest, work + 0.5 * longest);
+            double c = std::max(longest, work + 0.5 * longest);
+            // a few waves: whole waves of latency-bound items (measured: 19 shots of the 192 x 265 grid at 63 items per shot are
+            // 1197 items = 2 waves and 91 us, at 48 items per shot 1 wave and 64 us).  The reconstruction kernel's items outside
+            // the interior + ring return at once and do not occupy a slot.
+            const double live = which == 1 ? std::min(1.0, (double)(d.nzA - 2 * d.nPml + 4) / d.nzA) : 1.0;
+            const double waves = ceil((n_in + n_ed) * nb * live / conc);
+            if (waves <= 3.0 && n_in + n_ed > 0)
+                c = std::max(c, waves * (n_in * it_i + n_ed * (le + 4 + 3.0) * edge_latc) / (n_in + n_ed));
             if (c < bestc - 1e-9) { bestc = c; best = Lz; Le = le; }
         }
     if (const char *e = getenv("SEPFWI_LZ")) { const int v = atoi(e); if (v >= 2) best = v; }
