@@ -46,7 +46,7 @@ def auto_batch(nz, nx, nPad, nSteps, nrec, nPml, with_adjoint, nshots, device):
     """Concurrent shots per launch: enough to give every launch a few million cells, within memory."""
     torch = _torch()
     cells = float((nz - nPad) * nx)
-    B = min(16, int(4.0e6 / cells) + 1)
+    B = min(32, int(4.0e6 / cells) + 1)      # small grids: one launch for the whole survey beats two (whole waves of latency-bound warps)
     ring = 10.0 * ((nz - nPad - 2 * nPml + 4) + (nx - 2 * nPml + 4))
     per = (5.0 * ring * nSteps * 4 + 29.0 * cells * 4 if with_adjoint else 13.0 * cells * 4) + 4.0 * nrec * nSteps * 4
     free = torch.cuda.mem_get_info(device)[0]
