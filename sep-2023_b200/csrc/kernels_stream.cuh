@@ -489,7 +489,17 @@ struct AdjWin {
 constexpr int AR_NARR = 10, AR_NST = 3;
 constexpr int AR_WARP_BYTES = AR_NARR * AR_NST * 512;          // 15 KB per warp
 constexpr size_t AR_SMEM = (size_t)SW_WPB * AR_WARP_BYTES;     // 60 KB per CTA
-enum { AA_SZ = 0, AA_SX, AA_SXZ, AA_OVZ, AA_OVX, AA_LAM, AA_MU, AA_MUA, AA_BYA, AA_BYB };   // rows r+2 (stresses), r, r-2 (buoyancies)
+// edge warps use the same 15 KB as 2 stages x 15 arrays: the five extra slots carry the old-time-level CPML memory that phase A
+// of the row consumes right away -- ncu showed 35 % of the edge warps' stall samples on the shuffles waiting for those in-line
+// loads.  A warp that touches the x strips takes its four x arrays, any other edge warp the z arrays of the row.
+constexpr int AR_NARR_E = 15, AR_NST_E = 2;
+static_assert(AR_NARR_E * AR_NST_E * 512 <= AR_WARP_BYTES, "edge ring must fit the interior ring");
+enum { AA_SZ = 0, AA_SX, AA_SXZ, AA_OVZ, AA_OVX, AA_LAM, AA_MU, AA_MUA, AA_BYA, AA_BYB,    // rows r+2 (stresses), r, r-2 (buoyancies)
+       AE_0, AE_1, AE_2, AE_3, AE_4 };
+// x-type warp: psrc P_VX_X, P_VZ_X (x windows of phase A), psrc P_SXX_X, P_SXZ_X (old values of the update), row r
+enum { AX_PVXX = AE_0, AX_PVZX = AE_1, AX_PSXXX = AE_2, AX_PSXZX = AE_3 };
+// z-type warp: psrc P_VX_Z row r+1, P_VZ_Z row r+2 (newest rows of the z windows), psrc P_SXZ_Z, P_SZZ_Z row r (old values)
+enum { AZ_PVXZ = AE_0, AZ_PVZZ = AE_1, AZ_PSXZZ = AE_2, AZ_PSZZZ = AE_3 };
 
 // residual injection into the freshly updated adjoint velocities of row r (all 128 columns of the warp)
 __device__ __forceinline__ void stream_adj_inject(const AdjCtx &k, const int r, float nvz[4], float nvx[4])
@@ -521,13 +531,25 @@ __device__ __forceinline__ void stream_adj_inject(const AdjCtx &k, const int r, 
 }
 
 // request the operands of the iteration whose phase-A row is r
+template <bool EDGE>
 __device__ __forceinline__ void stream_adj_issue(const AdjCtx &k, const int r, const int stage)
 {
+    constexpr int NARR = EDGE ? AR_NARR_E : AR_NARR;
     const int ld = k.ld, nzA = k.nzA;
     const size_t fsz = k.fsz;
     auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };
     const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
-    const unsigned sb = k.ring_s + (unsigned)stage * (AR_NARR * 512);
+    const unsigned sb = k.ring_s + (unsigned)stage * (NARR * 512);
+    if (EDGE) {
+        const bool rowact = (r >= 2 && r <= nzA - 3);
+        if (k.xany) {
+            if (rowact && k.xsl) { cp16(sb + AX_PVXX * 512, k.psrc + (size_t)P_VX_X * fsz + r0); cp16(sb + AX_PVZX * 512, k.psrc + (size_t)P_VZ_X * fsz + r0); }
+            if (rowact && k.xpl) { cp16(sb + AX_PSXXX * 512, k.psrc + (size_t)P_SXX_X * fsz + r0); cp16(sb + AX_PSXZX * 512, k.psrc + (size_t)P_SXZ_X * fsz + r0); }
+        } else if (rowact && ((r < k.nPml) || (r > nzA - k.nPml - 1))) {
+            cp16(sb + AZ_PVXZ * 512, k.psrc + (size_t)P_VX_Z * fsz + r0 + ld); cp16(sb + AZ_PVZZ * 512, k.psrc + (size_t)P_VZ_Z * fsz + r0 + 2 * ld);
+            cp16(sb + AZ_PSXZZ * 512, k.psrc + (size_t)P_SXZ_Z * fsz + r0); cp16(sb + AZ_PSZZZ * 512, k.psrc + (size_t)P_SZZ_Z * fsz + r0);
+        }
+    }
     cp16(sb + AA_SZ * 512, k.g + F_SZZ * fsz + r2); cp16(sb + AA_SX * 512, k.g + F_SXX * fsz + r2); cp16(sb + AA_SXZ * 512, k.g + F_SXZ * fsz + r2);
     cp16(sb + AA_OVZ * 512, k.g + F_VZ * fsz + r0); cp16(sb + AA_OVX * 512, k.g + F_VX * fsz + r0);
     cp16(sb + AA_LAM * 512, k.m + M_LAM * fsz + r0); cp16(sb + AA_MU * 512, k.m + M_MU * fsz + r0); cp16(sb + AA_MUA * 512, k.m + M_MUAVE * fsz + r0);
@@ -542,9 +564,10 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
     const size_t fsz = k.fsz;
     const float c1z = k.c1z, c2z = k.c2z, c1x = k.c1x, c2x = k.c2x, dt = k.dt;
     constexpr int u = U;
-    stream_adj_issue(k, r + (AR_NST - 1), stage == 0 ? AR_NST - 1 : stage - 1);
-    cp_wait<AR_NST - 1>();
-    const float4 *sb = k.ring_p + stage * (AR_NARR * 32);
+    constexpr int NST = EDGE ? AR_NST_E : AR_NST, NARR = EDGE ? AR_NARR_E : AR_NARR;
+    stream_adj_issue<EDGE>(k, r + (NST - 1), stage == 0 ? NST - 1 : stage - 1);
+    cp_wait<NST - 1>();
+    const float4 *sb = k.ring_p + stage * (NARR * 32);
     w.sz[(u + 4) % 6] = sb[AA_SZ * 32]; w.sx[(u + 4) % 6] = sb[AA_SX * 32]; w.sxz[(u + 4) % 6] = sb[AA_SXZ * 32];     // row r+2
     // ---- phase A: adjoint velocities at row r from the old adjoint stresses, rows r-2 .. r+2 (slots u .. u+4)
     {
@@ -586,15 +609,15 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             float dpx[4] = {0.f, 0.f, 0.f, 0.f}, dpz[4] = {0.f, 0.f, 0.f, 0.f};     // a-weighted stencils of the old memory variables
             if (k.xany) {      // warp-uniform: shuffles inside
                 const bool xld = rowact && k.xsl;      // the stencils reach two columns into the kept strip (nPml + 2 wide)
-                const float4 pa = xld ? ldq(k.psrc + (size_t)P_VX_X * fsz + ro) : zero4, pb = xld ? ldq(k.psrc + (size_t)P_VZ_X * fsz + ro) : zero4;
+                const float4 pa = xld ? sb[AX_PVXX * 32] : zero4, pb = xld ? sb[AX_PVZX * 32] : zero4;     // prefetched with the row's operands
                 const float wa[7] = XWIN_F(pa), wb[7] = XWIN_B(pb);
 #pragma unroll
                 for (int c = 0; c < 4; c++) { dpx[c] = ax[c] * -DX7(wa, c); dpz[c] = axh[c] * -DX7(wb, c); }
             }
             if (zp) {
                 const float *pz0 = k.psrc + (size_t)P_VX_Z * fsz + ro, *pz1 = k.psrc + (size_t)P_VZ_Z * fsz + ro;
-                const float4 t0 = ldq(pz0 - 2 * ld), t1 = ldq(pz0 - ld), t2 = ldq(pz0), t3 = ldq(pz0 + ld);
-                const float4 s0 = ldq(pz1 - ld), s1 = ldq(pz1), s2 = ldq(pz1 + ld), s3 = ldq(pz1 + 2 * ld);
+                const float4 t0 = ldq(pz0 - 2 * ld), t1 = ldq(pz0 - ld), t2 = ldq(pz0), t3 = k.xany ? ldq(pz0 + ld) : sb[AZ_PVXZ * 32];
+                const float4 s0 = ldq(pz1 - ld), s1 = ldq(pz1), s2 = ldq(pz1 + ld), s3 = k.xany ? ldq(pz1 + 2 * ld) : sb[AZ_PVZZ * 32];
                 const float a0[4] = Q4(t0), a1[4] = Q4(t1), a2[4] = Q4(t2), a3[4] = Q4(t3), b0[4] = Q4(s0), b1[4] = Q4(s1), b2[4] = Q4(s2), b3[4] = Q4(s3);
 #pragma unroll
                 for (int c = 0; c < 4; c++) { dpx[c] += azh * -DZ4(a0[c], a1[c], a2[c], a3[c]); dpz[c] += az * -DZ4(b0[c], b1[c], b2[c], b3[c]); }
@@ -622,7 +645,7 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
                 if (xl && vm) {
                     const float4 f0 = ldq_c(k.cxa + C_BH * ld), f1 = ldq_c(k.cxa + C_B * ld);
                     const float bxh[4] = Q4(f0), bx[4] = Q4(f1);
-                    const float4 o0 = ldq(k.psrc + (size_t)P_SXX_X * fsz + ro), o1 = ldq(k.psrc + (size_t)P_SXZ_X * fsz + ro);
+                    const float4 o0 = sb[AX_PSXXX * 32], o1 = sb[AX_PSXZX * 32];      // xl implies an x-type warp
                     float n0[4] = Q4(o0), n1[4] = Q4(o1);
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
@@ -635,7 +658,8 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
                     stq_halo(k.pdst + (size_t)P_SXX_X * fsz + ro, n0, k.lane); stq_halo(k.pdst + (size_t)P_SXZ_X * fsz + ro, n1, k.lane);
                 }
                 if (zp && vm) {
-                    const float4 o0 = ldq(k.psrc + (size_t)P_SXZ_Z * fsz + ro), o1 = ldq(k.psrc + (size_t)P_SZZ_Z * fsz + ro);
+                    const float4 o0 = k.xany ? ldq(k.psrc + (size_t)P_SXZ_Z * fsz + ro) : sb[AZ_PSXZZ * 32],
+                                 o1 = k.xany ? ldq(k.psrc + (size_t)P_SZZ_Z * fsz + ro) : sb[AZ_PSZZZ * 32];
                     float n0[4] = Q4(o0), n1[4] = Q4(o1);
 #pragma unroll
                     for (int c = 0; c < 4; c++)
@@ -812,7 +836,7 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
         w.sz[j] = ldq(k.g + F_SZZ * fsz + ro); w.sx[j] = ldq(k.g + F_SXX * fsz + ro); w.sxz[j] = ldq(k.g + F_SXZ * fsz + ro);
     }
 #pragma unroll
-    for (int j = 0; j < AR_NST - 1; j++) stream_adj_issue(k, r0 + j, j);
+    for (int j = 0; j < (EDGE ? AR_NST_E : AR_NST) - 1; j++) stream_adj_issue<EDGE>(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
     if (!EDGE) {
 #pragma unroll 1
@@ -826,7 +850,7 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
 #pragma unroll 1
         for (int kk = 0; kk < niter; kk++) {
             stream_adj_row<EDGE, 0>(k, w, r0 + kk, stg);
-            stg = stg == AR_NST - 1 ? 0 : stg + 1;
+            stg = stg == AR_NST_E - 1 ? 0 : stg + 1;
 #pragma unroll
             for (int j = 0; j < 4; j++) { w.sz[j] = w.sz[j + 1]; w.sx[j] = w.sx[j + 1]; w.sxz[j] = w.sxz[j + 1]; }
             w.vz[2] = w.vz[3]; w.vz[3] = w.vz[4]; w.vz[4] = w.vz[5]; w.vz[5] = w.vz[0];
