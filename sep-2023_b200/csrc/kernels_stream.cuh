@@ -484,6 +484,7 @@ struct AdjCtx {
 struct AdjWin {
     float4 sz[6], sx[6], sxz[6];      // old adjoint stresses, rows r-2 .. r+2
     float4 vz[6], vx[6];              // new adjoint velocities, rows r-4 .. r
+    float4 qxx[3], qxz[3];            // edge warps: new x CPML memory (P_SXX_X, P_SXZ_X) of rows r-2 .. r, phase B's x windows
 };
 // operand ring (same scheme as the forward kernel): ten row quads per iteration, requested AR_NST-1 rows ahead
 constexpr int AR_NARR = 10, AR_NST = 3;
@@ -635,6 +636,7 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             // CPML memory of the adjoint velocities (strips only, from the velocities BEFORE the injection).  Written for every
             // column whose stencil window is complete (lane 0 comps 2,3 .. lane 31 comps 0,1): phase B reads them back, and the
             // neighbouring warps that recompute the same halo cells write the same values.
+            w.qxx[2] = zero4; w.qxz[2] = zero4;      // what phase B would read back from pdst two rows later (zero outside the x strips)
             if (xl || zp) {
                 const float4 bar4 = ldq(k.m + M_BYCA * fsz + ro), bbr4 = ldq(k.m + M_BYCB * fsz + ro);
                 const float bar[4] = Q4(bar4), bbr[4] = Q4(bbr4);
@@ -656,6 +658,7 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
                         }
                     }
                     stq_halo(k.pdst + (size_t)P_SXX_X * fsz + ro, n0, k.lane); stq_halo(k.pdst + (size_t)P_SXZ_X * fsz + ro, n1, k.lane);
+                    w.qxx[2] = mk4(n0); w.qxz[2] = mk4(n1);
                 }
                 if (zp && vm) {
                     const float4 o0 = k.xany ? ldq(k.psrc + (size_t)P_SXZ_Z * fsz + ro) : sb[AZ_PSXZZ * 32],
@@ -716,7 +719,7 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             float dxz[4] = {0.f, 0.f, 0.f, 0.f}, dxx[4] = {0.f, 0.f, 0.f, 0.f}, dzz[4] = {0.f, 0.f, 0.f, 0.f};
             if (k.xany) {      // x stencils of the memory variables written in phase A of this and earlier rows (plain loads: same-warp data)
                 const bool xld = rowact && k.xsl;
-                const float4 pa = xld ? ldq_rw(k.pdst + (size_t)P_SXZ_X * fsz + ro) : zero4, pb = xld ? ldq_rw(k.pdst + (size_t)P_SXX_X * fsz + ro) : zero4;
+                const float4 pa = xld ? w.qxz[0] : zero4, pb = xld ? w.qxx[0] : zero4;      // this warp's own phase-A values of row q = r-2
                 const float wa[7] = XWIN_F(pa), wb[7] = XWIN_B(pb);
 #pragma unroll
                 for (int c = 0; c < 4; c++) { dxz[c] = ax[c] * -DX7(wa, c); dxx[c] = axh[c] * -DX7(wb, c); }
@@ -828,6 +831,8 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 6; j++) { w.sz[j] = w.sx[j] = w.sxz[j] = w.vz[j] = w.vx[j] = zero; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { w.qxx[j] = w.qxz[j] = zero; }
     auto rowoff = [&](int row) { return (size_t)min(max(row, 0), d.nzA - 1) * d.ldx; };
     const int r0 = k.zc0 - 2;
 #pragma unroll
@@ -855,6 +860,7 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
             for (int j = 0; j < 4; j++) { w.sz[j] = w.sz[j + 1]; w.sx[j] = w.sx[j + 1]; w.sxz[j] = w.sxz[j + 1]; }
             w.vz[2] = w.vz[3]; w.vz[3] = w.vz[4]; w.vz[4] = w.vz[5]; w.vz[5] = w.vz[0];
             w.vx[3] = w.vx[4]; w.vx[4] = w.vx[5]; w.vx[5] = w.vx[0];
+            w.qxx[0] = w.qxx[1]; w.qxx[1] = w.qxx[2]; w.qxz[0] = w.qxz[1]; w.qxz[1] = w.qxz[2];
         }
     }
     cp_wait<0>();
