@@ -724,13 +724,26 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
             (is_edge ? edge : inner).push_back(make_int4(sx * SW_OWN, a0, a1, is_edge ? 1 : 0));
         }
     };
+    // adjoint sweep: strips that hold residual-injection targets (a vertical fiber puts targets on every row of one strip) are
+    // slower per row (staging + dependent table loads): half-height chunks, listed first, so they do not form the tail
+    std::vector<char> heavy(nStrips, 0);
+    if (which == 2)
+        for (int s_ = 0; s_ < nb; s_++)
+            for (int sx = 0; sx < nStrips; sx++) {
+                const int *sp = h->h_int + h->o_sInjPtr + ((size_t)s_ * h->nStrips + sx) * (d.nzA + 1);
+                int rows = 0;
+                for (int z = zi0; z < zi1; z++) rows += sp[z + 1] > sp[z] ? 1 : 0;
+                if (4 * rows >= zi1 - zi0) heavy[sx] = 1;      // targets on a quarter of the interior rows or more
+            }
     for (int sx = 0; sx < nStrips; sx++) { split(0, zi0, Le, sx, true); split(zi1, d.nzA, Le, sx, true); }
     for (int sx = 0; sx < nStrips; sx++) {
-        if (strip_inner(sx)) split(zi0, zi1, best, sx, false);
+        if (strip_inner(sx)) split(zi0, zi1, heavy[sx] ? std::max(8, best / 2) : best, sx, false);
         else split(zi0, zi1, Le, sx, true);
     }
-    // interior items: chunk-major so that concurrently running warps read neighbouring strips of the same rows
-    std::stable_sort(inner.begin(), inner.end(), [](const int4 &p, const int4 &q) { return p.y < q.y; });
+    // interior items: chunk-major so that concurrently running warps read neighbouring strips of the same rows; heavy strips first
+    std::stable_sort(inner.begin(), inner.end(), [&](const int4 &p, const int4 &q) {
+        const int hp = heavy[p.x / SW_OWN] ? 0 : 1, hq = heavy[q.x / SW_OWN] ? 0 : 1;
+        return hp != hq ? hp < hq : p.y < q.y; });
     edge.insert(edge.end(), inner.begin(), inner.end());
     if (edge.size() > h->work_cap[which]) {
         if (h->work[which]) cudaFree(h->work[which]);
