@@ -10,8 +10,11 @@
 //     z stencils come from register windows, x stencils from conflict-free shared-memory reads;
 //   * a time step is  stress on own + 2 ring cells (recomputed instead of exchanged)  ->  barrier  ->  velocity on
 //     the own cells  ->  publish the own cells within 4 of the tile edge to the global ping-pong velocity arrays
-//     ->  release a per-tile step counter  ->  acquire the neighbours' counters and pull the 4-cell velocity halo
-//     back into shared memory.  One neighbour exchange per step, no grid-wide barrier, no launch;
+//     (st.cg)  ->  barrier  ->  lanes of warp 0 fence and write the step number into the eight neighbours' inbox lines
+//     ->  every warp polls its OWN tile's inbox line (relaxed loads: no L1 invalidation, no two tiles on one line) and
+//     pulls its share of the 4-cell velocity halo from L2 (ld.cg)  ->  barrier.  One neighbour exchange per step, no
+//     grid-wide barrier, no launch.  Measured alternatives (acquire loads, a shared counter line, tagged 64-bit words,
+//     overlapping the exchange with the inner stress rows) are listed in profiles/README.md;
 //   * traces, the explosive source and the boundary-ring save (reference layout, bit-exact) run inside the same
 //     phases from shared memory: v-derived samples and the v ring while v is read-only (stress phase), the
 //     pressure sample and the sigma ring while sigma is read-only (velocity phase).
@@ -35,7 +38,7 @@ constexpr int RS_FLAGW = 32;     // ints per tile inbox (one 128-byte line)
 
 struct ResArgs {
     int ntx, ntz, slot0;         // tiles; first slot of this launch (blockIdx.y = slot - slot0)
-    int orows;                   // own rows of a tile, <= 8 RPT - 8
+    int orows;                   // own rows of a tile, <= RS_NG RPT - 8
     int mask, fiber, save_ring;
     int dbg;                     // timing experiments only (SEPFWI_RES_DEBUG): 1 no exchange wait, 2 no stress phase, 4 no velocity phase, 8 no fence + flag, 16 no v traces
     int *flags;                  // [gridDim.y][ntx*ntz][RS_FLAGW] inboxes: slot (dz+1)*3+(dx+1) = steps completed by the neighbour in direction
@@ -50,14 +53,10 @@ struct ResArgs {
 __host__ __device__ constexpr size_t rs_smem_bytes(int RPT)
 { return sizeof(float) * ((size_t)5 * RS_NG * RPT * RS_EW + 4 * RS_PW * RS_EW + (size_t)4 * RS_NG * RPT * RS_PW + 6 * RS_NG * RPT); }
 
-__device__ __forceinline__ int rs_ld_acquire(const int *p)
-{ int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ int rs_ld_relaxed(const int *p)
 { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void rs_st_relaxed(int *p, int v)
 { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void rs_st_release(int *p, int v)
-{ asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // traces derived from the velocities (sample `samp` = the state now in shared memory)
 template <int ER>
