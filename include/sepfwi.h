@@ -148,7 +148,11 @@ int sepfwi_ring_restore(sepfwi_handle *h, float *field, const float *bnd);
  * since creation, and device time of the last forward / backward time loops in ms. */
 int sepfwi_get_cpml(sepfwi_handle *h, int axis /*0=z,1=x*/, float *out6xN);
 long long sepfwi_launch_count(sepfwi_handle *h);
-long long sepfwi_resident_launches(sepfwi_handle *h);   /* cooperative launches of the resident forward loop so far */
+long long sepfwi_resident_launches(sepfwi_handle *h);
+/* Host-only: the tiling the resident forward loop would use for `nshots` concurrent shots on a device with `nsm` SMs and
+ * `smem_optin` bytes of opt-in shared memory per block; out = {rows per thread (0 = streaming kernels instead), tiles in x,
+ * tiles in z, own rows per tile, shots per cooperative launch}.  Makes no CUDA call. */
+int sepfwi_plan_resident(const sepfwi_params *p, int nshots, int nsm, size_t smem_optin, int out[5]);   /* cooperative launches of the resident forward loop so far */
 int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
 
 /* Per-kernel device timing: with nsteps > 0 every launch of the first nsteps time steps of each

@@ -824,6 +824,25 @@ static ResPlan resident_plan(const sepfwi_handle *h, int nb)
     return best;
 }
 
+// The tiling `sepfwi_forward` would use for `nshots` concurrent shots on a device with `nsm` SMs and `smem_optin` bytes of
+// opt-in shared memory per block -- pure host arithmetic (no CUDA call), exposed so that the planner can be tested without a GPU.
+// out = {rows per thread (0: streaming kernels), tiles in x, tiles in z, own rows per tile, shots per launch}
+extern "C" int sepfwi_plan_resident(const sepfwi_params *pp, int nshots, int nsm, size_t smem_optin, int out[5])
+{
+    if (!pp || !out || nshots < 1 || nsm < 1) return fail(SEPFWI_EINVAL, "bad argument");
+    sepfwi_handle h;
+    h.p = *pp;
+    int rc = fill_dims(*pp, h.d);
+    if (rc) return rc;
+    h.nSM = nsm; h.smem_optin = smem_optin;
+    h.sponge = pp->flavour == SEPFWI_FLAVOUR_SPONGE;
+    h.stream = !h.sponge && (pp->kernels == 0 || pp->kernels == 3);
+    h.resident = h.stream && pp->kernels == 0 && h.d.nPml <= RS_PW;
+    const ResPlan pl = resident_plan(&h, nshots);
+    out[0] = pl.rpt; out[1] = pl.ntx; out[2] = pl.ntz; out[3] = pl.orows; out[4] = pl.per_launch;
+    return 0;
+}
+
 static void ring_cell_host(const Dims &d, int idx, int &z, int &x)       // inverse of the ring map, as kernels_base.cuh ring_cell
 {
     const int L = 5;

@@ -461,3 +461,37 @@ def test_ragged_and_empty_receiver_sets(kernels):
     for k in ("glam", "gmu", "grho"):
         assert rel_l2(a[1][k], b[1][k]) < 1e-4, k
     assert np.all(a[1]["gstf"][2] == b[1]["gstf"][2])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_resident_forward_on_random_grids(seed):
+    """Random grid sizes, CPML widths, batch sizes, source / receiver positions: whatever tiling the planner picks (tile heights
+    that do not divide the grid, partial last tiles in x and z, several shots per launch, sources and receivers on tile edges),
+    the resident forward loop must reproduce the unfused baseline kernels; grids it refuses run the streaming kernels."""
+    _, Propagator, ShotSpec = _mods()
+    rng = np.random.default_rng(100 + seed)
+    nPml = int(rng.choice([8, 16, 32]))
+    nzo, nxo = int(rng.integers(40, 260)), int(rng.integers(60, 700))
+    NZ, NX, nPad = problems.pad_rule(nzo, nxo, nPml)
+    nt, nb = 70, int(rng.integers(1, 5))
+    vp = problems.layered_vp(nzo, nxo, 1800.0, 3600.0, 5, rng, nlens=8, lens_amp=0.1, sigma=(3, 12))
+    model = problems.lame_from_vp(problems.pad_model(vp, nPml, nPad))
+    stf = problems.ricker(25.0, nt, 1.0e-3)
+    shots = []
+    for _ in range(nb):
+        nrec = int(rng.integers(1, 40))
+        zs, xs = int(rng.integers(2, nzo - 2)) + nPml, int(rng.integers(2, nxo - 2)) + nPml
+        # receivers within ~25 cells of the source so that the 70-step wavefield reaches them; clipped to the recordable range
+        zr = np.clip(zs + rng.integers(-25, 26, nrec), 1, NZ - nPad - 2)
+        xr = np.clip(xs + rng.integers(-25, 26, nrec), 1, NX - 2)
+        shots.append(ShotSpec(zs, xs, zr, xr, stf))
+    res = {}
+    for kern in (0, 1):
+        with Propagator(NZ, NX, nPml, nPad, nt, 10.0, 10.0, 1.0e-3, 25.0, max_batch=nb, max_nrec=40, device=0, kernels=kern) as P:
+            P.set_model(*model)
+            res[kern] = (P.forward(shots), P.resident_launches)
+    for k in range(nb):
+        for c in ("pr", "vx", "vz", "ett"):
+            ref = res[1][0][k][c]
+            if np.abs(ref).max() > 0:
+                assert rel_l2(res[0][0][k][c], ref) < 1e-5, (seed, NZ, NX, nPml, nb, k, c, res[0][1])

@@ -220,3 +220,50 @@ def test_pytorch_objective_drives_scipy_lbfgs():
                           options={"maxiter": 50, "maxcor": 5, "ftol": 1e-14, "gtol": 1e-10})
     assert np.allclose(r.x[:12], np.arange(12), atol=1e-4) and np.allclose(r.x[12:], 0.5)    # B sits on its lower bound
     assert np.allclose(m.B.detach().numpy(), obj.unpack_parameters(obj.cached_x)["B"].numpy())
+
+
+def test_resident_planner_invariants_over_many_grids():
+    """sepfwi_plan_resident (host arithmetic only): for every grid it accepts, the tiles cover the live grid, fit the SMs, the
+    per-tile shared memory fits the device limit, no tile spans both sides of a CPML strip pair (it holds the memory variables of
+    one z side and one x side only), and the batch is split into whole launches.  Known plans: C2 -> 19 x 7 tiles of 67 rows, rows
+    per thread 10; C3 and the 8000 x 2000 grid do not fit 148 SMs; the reference-size grid takes several shots per launch."""
+    import ctypes as C
+    from sepfwi import _lib
+    L = _lib.lib()
+
+    def plan(nz, nx, nPml, nPad, nshots, nsm=148, smem=232448, kernels=0):
+        p = _lib.Params(nz, nx, nPml, nPad, 100, 10.0, 10.0, 1e-3, 10.0, 0, 0, nshots, 1, 0, kernels, 0)
+        out = (C.c_int * 5)()
+        assert L.sepfwi_plan_resident(C.byref(p), nshots, nsm, smem, out) == 0
+        return tuple(out)
+
+    assert plan(480, 1064, 32, 16, 1) == (10, 19, 7, 67, 1)                 # C2
+    assert plan(416, 1764, 32, 2, 1)[0] == 0 and plan(2080, 8064, 32, 32, 1)[0] == 0
+    rpt, ntx, ntz, orows, per = plan(192, 265, 32, 32, 19)                  # the reference's experiment, 19 shots
+    assert rpt > 0 and per >= 4 and ntx == 5
+    assert plan(480, 1064, 32, 16, 1, kernels=3)[0] == 0                    # streaming kernels forced
+    assert plan(480, 1064, 32, 16, 1, nsm=64)[0] == 0                       # a smaller device cannot co-schedule the tiles
+    assert plan(480, 1064, 32, 16, 1, smem=100 * 1024)[0] == 0              # ... nor one with little shared memory
+    rng = np.random.default_rng(1)
+    accepted = 0
+    for _ in range(400):
+        nPml = int(rng.choice([8, 16, 32]))
+        nzo, nxo = int(rng.integers(12, 500)), int(rng.integers(12, 1500))
+        nPad = int(32 - (nzo + 2 * nPml) % 32)
+        nz, nx, nb = nzo + 2 * nPml + nPad, nxo + 2 * nPml, int(rng.integers(1, 20))
+        rpt, ntx, ntz, orows, per = plan(nz, nx, nPml, nPad, nb)
+        if rpt == 0:
+            continue
+        accepted += 1
+        nzA, ER = nz - nPad, 8 * rpt
+        assert 3 <= rpt <= 13 and 4 <= orows <= ER - 8
+        assert ntx * 56 >= nx and (ntx - 1) * 56 < nx and ntz * orows >= nzA and (ntz - 1) * orows < nzA
+        assert 1 <= per <= nb and ntx * ntz * per <= 148
+        assert 4 * (5 * ER * 64 + 4 * 32 * 64 + 4 * ER * 32 + 6 * ER) <= 232448
+        for t in range(ntz):
+            lo, hi = max(t * orows - 4, 0), min(t * orows - 4 + ER - 1, nzA - 1)
+            assert not (lo < nPml and hi > nzA - nPml - 1), (nz, nx, nPml, t)
+        for t in range(ntx):
+            lo, hi = max(t * 56 - 4, 0), min(t * 56 + 59, nx - 1)
+            assert not (lo < nPml and hi > nx - nPml - 1), (nz, nx, nPml, t)
+    assert accepted > 50
