@@ -485,13 +485,24 @@ def test_resident_forward_on_random_grids(seed):
         zr = np.clip(zs + rng.integers(-25, 26, nrec), 1, NZ - nPad - 2)
         xr = np.clip(xs + rng.integers(-25, 26, nrec), 1, NX - 2)
         shots.append(ShotSpec(zs, xs, zr, xr, stf))
+    start = problems.lame_from_vp(problems.pad_model(problems.smooth(vp, 5), nPml, nPad))
     res = {}
     for kern in (0, 1):
-        with Propagator(NZ, NX, nPml, nPad, nt, 10.0, 10.0, 1.0e-3, 25.0, max_batch=nb, max_nrec=40, device=0, kernels=kern) as P:
+        with Propagator(NZ, NX, nPml, nPad, nt, 10.0, 10.0, 1.0e-3, 25.0, max_batch=nb, max_nrec=40, with_adjoint=True, device=0,
+                        kernels=kern) as P:
             P.set_model(*model)
-            res[kern] = (P.forward(shots), P.resident_launches)
+            fwd = P.forward(shots)
+            P.set_model(*start)
+            res[kern] = (fwd, P.resident_launches, P.gradient(shots, [f["ett"] for f in fwd]))
     for k in range(nb):
         for c in ("pr", "vx", "vz", "ett"):
             ref = res[1][0][k][c]
             if np.abs(ref).max() > 0:
                 assert rel_l2(res[0][0][k][c], ref) < 1e-5, (seed, NZ, NX, nPml, nb, k, c, res[0][1])
+    # the gradient's forward pass also ran resident: its boundary ring (per-tile entry lists) and final state feed the streaming
+    # reverse-time kernels
+    ga, gb = res[0][2], res[1][2]
+    if abs(gb["misfit"]) > 0:
+        assert abs(ga["misfit"] - gb["misfit"]) <= 1e-5 * abs(gb["misfit"])
+        for k in ("glam", "gmu", "grho"):
+            assert rel_l2(ga[k], gb[k]) < 1e-4, (seed, k, res[0][1])
