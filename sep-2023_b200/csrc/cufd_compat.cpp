@@ -149,7 +149,7 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
     if (!js.ok || survey.kind != JVal::Obj) return efail(SEPFWI_EIO, "survey file is not a JSON object");
 
     const int nS = (int)nSteps, npml = (int)nPml;
-    struct ShotData { std::vector<int> zr, xr; std::vector<float> obs, out[4], gstf; };
+    struct ShotData { std::vector<int> zr, xr; std::vector<float> obs, out[4], gstf, w; };
     std::vector<ShotData> sd(group_size);
     std::vector<sepfwi_shot> shots(group_size);
     int maxrec = 1;
@@ -168,6 +168,17 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
         sh.zs = (int)zs->num + npml; sh.xs = (int)xs->num + npml;                                                               // Src_Rec.cu:87,92
         sh.nrec = nrec; sh.zrec = sd[i].zr.data(); sh.xrec = sd[i].xr.data();
         sh.stf = stf + (size_t)shot_ids[i] * nS;                                                                                // Src_Rec.cu:132
+        // extension: per-channel (exx, ezz, exz) sensitivities, "das_sensitivity": [[w0, w1, w2], ...]
+        if (const JVal *ds = s->get("das_sensitivity")) {
+            if (ds->kind != JVal::Arr || (int)ds->arr.size() < nrec) return efail(SEPFWI_EIO, key + ": das_sensitivity needs nrec rows");
+            sd[i].w.resize((size_t)3 * nrec);
+            for (int r = 0; r < nrec; r++) {
+                const JVal &row = ds->arr[r];
+                if (row.kind != JVal::Arr || row.arr.size() < 3) return efail(SEPFWI_EIO, key + ": das_sensitivity rows are [exx, ezz, exz]");
+                for (int c = 0; c < 3; c++) sd[i].w[(size_t)3 * r + c] = (float)row.arr[c].num;
+            }
+            sh.weights = sd[i].w.data();
+        }
         const JVal *rxz = s->get("src_rxz");
         sh.src_rxz = rxz && rxz->kind == JVal::Num ? (float)rxz->num : 1.0f;                                                     // RSXXZZ, utilities.h:21
         maxrec = nrec > maxrec ? nrec : maxrec;

@@ -506,3 +506,52 @@ def test_resident_forward_on_random_grids(seed):
         assert abs(ga["misfit"] - gb["misfit"]) <= 1e-5 * abs(gb["misfit"])
         for k in ("glam", "gmu", "grho"):
             assert rel_l2(ga[k], gb[k]) < 1e-4, (seed, k, res[0][1])
+
+
+def test_cufd_dropin_reads_das_sensitivity(tmp_path):
+    """The C drop-in (sepfwi_cufd) honours "das_sensitivity" in survey_file.json like the Python op: rows (1, 0, 0) reproduce
+    the stock horizontal fiber bit-exactly, an oriented fiber equals the Python front-end on the same files."""
+    import torch
+    from sepfwi import _lib, fwi_ops, fwi_utils as ft
+    prob = problems.tiny()
+    ids = np.arange(prob.nshots, dtype=np.int32)
+    nrec = len(prob.x_rec)
+    rng = np.random.default_rng(9)
+    ang = rng.uniform(0, np.pi, nrec)
+    oriented = np.stack([np.cos(ang) ** 2, np.sin(ang) ** 2, 2 * np.sin(ang) * np.cos(ang)], 1)
+
+    def run(tag, sens, python_op=False):
+        work = str(tmp_path / tag)
+        os.makedirs(work)
+        para, survey, data = work + "/para.json", work + "/survey.json", work + "/d"
+        ft.paraGen(prob.nz, prob.nx, prob.dz, prob.dx, prob.nSteps, prob.dt, prob.f0, prob.nPml, prob.nPad, para, survey, data)
+        ft.surveyGen(prob.z_src, prob.x_src, prob.z_rec, prob.x_rec, survey, Das_sensitivity=sens)
+        stf = np.ascontiguousarray(prob.stf, np.float32)
+        if python_op:
+            T = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32))
+            tids = torch.from_numpy(ids)
+            fwi_ops.obscalc(*map(T, prob.true), T(stf), 1, tids, para)
+            out = fwi_ops.backward(*map(T, prob.start), T(stf), 1, tids, para)
+            return out[0].item(), out[1].numpy(), out[2].numpy(), out[3].numpy()
+        p = lambda a: a.ctypes.data
+
+        def call(calc_id, model):
+            lam, mu, den = (np.ascontiguousarray(a, np.float32) for a in model)
+            J = np.zeros(1, np.float32)
+            g = [np.zeros_like(lam) for _ in range(3)]
+            gs = np.zeros_like(stf)
+            _lib.check(_lib.lib().sepfwi_cufd(p(J), p(g[0]), p(g[1]), p(g[2]), p(gs), p(lam), p(mu), p(den), p(stf),
+                                               calc_id, 0, ids.size, p(ids), para.encode()))
+            return float(J[0]), g[0], g[1], g[2]
+        call(2, prob.true)
+        return call(1, prob.start)
+
+    stock, exx = run("stock", None), run("exx", np.tile([1.0, 0.0, 0.0], (nrec, 1)))
+    assert stock[0] == exx[0] and all(np.array_equal(a, b) for a, b in zip(stock[1:], exx[1:]))
+    c_side, py_side = run("oriented_c", oriented), run("oriented_py", oriented, python_op=True)
+    assert abs(c_side[0] - stock[0]) > 0.05 * abs(stock[0])
+    assert abs(c_side[0] - py_side[0]) <= 1e-6 * abs(py_side[0])
+    for a, b in zip(c_side[1:], py_side[1:]):
+        assert rel_l2(a, b) < 1e-6
+    _lib.lib().sepfwi_cufd_clear_cache()
+    fwi_ops.clear_cache()
