@@ -152,7 +152,10 @@ long long sepfwi_resident_launches(sepfwi_handle *h);
 /* Host-only: the tiling the resident forward loop would use for `nshots` concurrent shots on a device with `nsm` SMs and
  * `smem_optin` bytes of opt-in shared memory per block; out = {rows per thread (0 = streaming kernels instead), tiles in x,
  * tiles in z, own rows per tile, shots per cooperative launch}.  Makes no CUDA call. */
-int sepfwi_plan_resident(const sepfwi_params *p, int nshots, int nsm, size_t smem_optin, int out[5]);   /* cooperative launches of the resident forward loop so far */
+int sepfwi_plan_resident(const sepfwi_params *p, int nshots, int nsm, size_t smem_optin, int out[5]);
+/* Host-only: the work list of streaming kernel `which` (0 forward, 1 reconstruction + imaging, 2 adjoint) -- one entry per warp,
+ * {first owned column, first row, end row, 1 if the warp takes the CPML path}; *n = number of entries (may exceed cap). */
+int sepfwi_plan_stream(const sepfwi_params *p, int nshots, int nsm, int which, int *items4, int cap, int *n);   /* cooperative launches of the resident forward loop so far */
 int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
 
 /* Per-kernel device timing: with nsteps > 0 every launch of the first nsteps time steps of each

@@ -668,7 +668,7 @@ static int max_nrec(int nb, const sepfwi_shot *shots)
 //     CPML memory variables, no look-ahead): they get shorter chunks and are listed first so they never form the tail;
 //   * interior chunks are Lz rows with (Lz + 4) a multiple of the 6-row unroll, Lz chosen so that the item count fills whole
 //     waves of nSM x 8 resident warps (2 CTAs x 4 warps at 255 registers).  SEPFWI_LZ / SEPFWI_LZE override the two heights.
-static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 adj*/, StreamArgs &sa)
+static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 adj*/, StreamArgs &sa, std::vector<int4> *items_out = nullptr)
 {
     const Dims &d = h->d;
     memset(&sa, 0, sizeof(sa));
@@ -727,7 +727,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     // adjoint sweep: strips that hold residual-injection targets (a vertical fiber puts targets on every row of one strip) are
     // slower per row (staging + dependent table loads): half-height chunks, listed first, so they do not form the tail
     std::vector<char> heavy(nStrips, 0);
-    if (which == 2)
+    if (which == 2 && h->h_int)
         for (int s_ = 0; s_ < nb; s_++)
             for (int sx = 0; sx < nStrips; sx++) {
                 const int *sp = h->h_int + h->o_sInjPtr + ((size_t)s_ * h->nStrips + sx) * (d.nzA + 1);
@@ -745,6 +745,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
         const int hp = heavy[p.x / SW_OWN] ? 0 : 1, hq = heavy[q.x / SW_OWN] ? 0 : 1;
         return hp != hq ? hp < hq : p.y < q.y; });
     edge.insert(edge.end(), inner.begin(), inner.end());
+    if (items_out) { *items_out = edge; return 0; }      // host-only planning (sepfwi_plan_stream): nothing is uploaded
     if (edge.size() > h->work_cap[which]) {
         if (h->work[which]) cudaFree(h->work[which]);
         h->work[which] = nullptr; h->work_cap[which] = 0;
@@ -840,6 +841,26 @@ extern "C" int sepfwi_plan_resident(const sepfwi_params *pp, int nshots, int nsm
     h.resident = h.stream && pp->kernels == 0 && h.d.nPml <= RS_PW;
     const ResPlan pl = resident_plan(&h, nshots);
     out[0] = pl.rpt; out[1] = pl.ntx; out[2] = pl.ntz; out[3] = pl.orows; out[4] = pl.per_launch;
+    return 0;
+}
+
+// Work list of the streaming kernel `which` (0 forward, 1 reconstruction, 2 adjoint) for `nshots` concurrent shots on a device
+// with `nsm` SMs -- host arithmetic only.  items: up to `cap` entries {first owned column, first row, end row, 1 if edge item};
+// *n receives the number of items the plan has (may exceed cap).
+extern "C" int sepfwi_plan_stream(const sepfwi_params *pp, int nshots, int nsm, int which, int *items, int cap, int *n)
+{
+    if (!pp || !n || nshots < 1 || nsm < 1 || which < 0 || which > 2 || (cap > 0 && !items)) return fail(SEPFWI_EINVAL, "bad argument");
+    sepfwi_handle h;
+    h.p = *pp;
+    int rc = fill_dims(*pp, h.d);
+    if (rc) return rc;
+    h.nSM = nsm;
+    StreamArgs sa;
+    std::vector<int4> v;
+    rc = stream_plan(&h, nshots, which, sa, &v);
+    if (rc) return rc;
+    *n = (int)v.size();
+    for (int i = 0; i < (int)v.size() && i < cap; i++) { items[4 * i] = v[i].x; items[4 * i + 1] = v[i].y; items[4 * i + 2] = v[i].z; items[4 * i + 3] = v[i].w; }
     return 0;
 }
 

@@ -267,3 +267,37 @@ def test_resident_planner_invariants_over_many_grids():
             lo, hi = max(t * 56 - 4, 0), min(t * 56 + 59, nx - 1)
             assert not (lo < nPml and hi > nx - nPml - 1), (nz, nx, nPml, t)
     assert accepted > 50
+
+
+def test_streaming_work_lists_tile_the_grid_exactly():
+    """sepfwi_plan_stream (host arithmetic only): for random grids, CPML widths and batch sizes the work list of each streaming
+    kernel covers every (row, 120-column strip) of the live grid exactly once, interior (branch-free) items keep the nPml + 5 margin
+    from every CPML strip, edge items come first, and no chunk is empty."""
+    import ctypes as C
+    from sepfwi import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(4)
+    for trial in range(120):
+        nPml = int(rng.choice([8, 16, 32]))
+        nzo, nxo = int(rng.integers(12, 2200)), int(rng.integers(12, 8100))
+        if trial % 3 == 0:
+            nzo, nxo = int(rng.integers(12, 300)), int(rng.integers(12, 600))
+        nPad = int(32 - (nzo + 2 * nPml) % 32)
+        nz, nx, nb = nzo + 2 * nPml + nPad, nxo + 2 * nPml, int(rng.integers(1, 20))
+        nzA, nstrips = nz - nPad, (nx + 119) // 120
+        p = _lib.Params(nz, nx, nPml, nPad, 100, 10.0, 10.0, 1e-3, 10.0, 0, 0, nb, 1, 0, 3, 0)
+        for which in range(3):
+            n = C.c_int(0)
+            assert L.sepfwi_plan_stream(C.byref(p), nb, 148, which, None, 0, C.byref(n)) == 0
+            buf = (C.c_int * (4 * n.value))()
+            assert L.sepfwi_plan_stream(C.byref(p), nb, 148, which, buf, n.value, C.byref(n)) == 0
+            it = np.frombuffer(buf, np.int32).reshape(-1, 4)
+            assert np.all(it[:, 0] % 120 == 0) and np.all(it[:, 2] > it[:, 1]) and np.all(it[:, 1] >= 0) and np.all(it[:, 2] <= nzA)
+            cover = np.zeros((nstrips, nzA), np.int32)
+            for x0, z0, z1, edge in it:
+                cover[x0 // 120, z0:z1] += 1
+                if not edge:
+                    assert z0 >= nPml + 5 and z1 <= nzA - nPml - 5 and x0 - 4 >= nPml + 3 and x0 + 123 <= nx - nPml - 4
+            assert np.all(cover == 1), (nz, nx, nPml, nb, which)
+            first_inner = np.argmax(it[:, 3] == 0) if np.any(it[:, 3] == 0) else len(it)
+            assert np.all(it[first_inner:, 3] == 0)                  # edge items first
