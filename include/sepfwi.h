@@ -71,7 +71,7 @@ typedef struct sepfwi_params {
     int   max_nrec;        /* upper bound of receivers per shot                                                        */
     int   with_adjoint;    /* 1: allocate boundary store + adjoint state (needed by sepfwi_gradient with_adj)          */
     int   kernels;         /* 0: default (shared-memory-resident forward loop where the tiles of a shot fit the SMs, register-streaming
-                              kernels otherwise), 1: unfused baseline kernels, 2: shared-memory tile kernels, 3: streaming kernels only */
+                              kernels otherwise), 1: unfused baseline kernels (cross-check), 3: streaming kernels only */
     int   ref_race_compat; /* 0 (default): race-free adjoint source.  1: reproduce the reference's lost update in
                               res_injection_exx/_ezz (utilities.cu:613-614,639-640, launched 32 receivers per block):
                               when receiver 32k subtracts at the cell receiver 32k-1 adds to, the subtraction is dropped.
@@ -148,23 +148,22 @@ int sepfwi_ring_restore(sepfwi_handle *h, float *field, const float *bnd);
  * since creation, and device time of the last forward / backward time loops in ms. */
 int sepfwi_get_cpml(sepfwi_handle *h, int axis /*0=z,1=x*/, float *out6xN);
 long long sepfwi_launch_count(sepfwi_handle *h);
-long long sepfwi_resident_launches(sepfwi_handle *h);
+long long sepfwi_resident_launches(sepfwi_handle *h);   /* cooperative launches of the resident forward loop so far */
 /* Host-only: the tiling the resident forward loop would use for `nshots` concurrent shots on a device with `nsm` SMs and
  * `smem_optin` bytes of opt-in shared memory per block; out = {rows per thread (0 = streaming kernels instead), tiles in x,
  * tiles in z, own rows per tile, shots per cooperative launch}.  Makes no CUDA call. */
 int sepfwi_plan_resident(const sepfwi_params *p, int nshots, int nsm, size_t smem_optin, int out[5]);
 /* Host-only: the work list of streaming kernel `which` (0 forward, 1 reconstruction + imaging, 2 adjoint) -- one entry per warp,
  * {first owned column, first row, end row, 1 if the warp takes the CPML path}; *n = number of entries (may exceed cap). */
-int sepfwi_plan_stream(const sepfwi_params *p, int nshots, int nsm, int which, int *items4, int cap, int *n);   /* cooperative launches of the resident forward loop so far */
+int sepfwi_plan_stream(const sepfwi_params *p, int nshots, int nsm, int which, int *items4, int cap, int *n);
 int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
 
 /* Per-kernel device timing: with nsteps > 0 every launch of the first nsteps time steps of each
  * time loop is bracketed by a CUDA-event pair on the launching stream; sepfwi_get_profile returns
  * accumulated milliseconds and launch counts per kernel kind since the last sepfwi_set_profile. */
 enum { SEPFWI_K_RING_SAVE = 0, SEPFWI_K_STRESS_FWD, SEPFWI_K_VELOCITY_FWD, SEPFWI_K_RECORD, SEPFWI_K_VELOCITY_BWD,
-       SEPFWI_K_STRESS_BWD, SEPFWI_K_VELOCITY_ADJ, SEPFWI_K_INJECT, SEPFWI_K_STRESS_ADJ, SEPFWI_K_FUSED_FWD,
-       SEPFWI_K_FUSED_RECON, SEPFWI_K_FUSED_ADJ, SEPFWI_K_STREAM_FWD, SEPFWI_K_STREAM_RECON, SEPFWI_K_STREAM_ADJ, SEPFWI_K_RESIDENT_FWD,
-       SEPFWI_NKERNEL };
+       SEPFWI_K_STRESS_BWD, SEPFWI_K_VELOCITY_ADJ, SEPFWI_K_INJECT, SEPFWI_K_STRESS_ADJ, SEPFWI_K_STREAM_FWD, SEPFWI_K_STREAM_RECON,
+       SEPFWI_K_STREAM_ADJ, SEPFWI_K_STREAM_BWD, SEPFWI_K_RESIDENT_FWD, SEPFWI_NKERNEL };
 int sepfwi_set_profile(sepfwi_handle *h, int nsteps);
 int sepfwi_get_profile(sepfwi_handle *h, double *ms /*[SEPFWI_NKERNEL]*/, long long *count /*[SEPFWI_NKERNEL]*/);
 const char *sepfwi_kernel_name(int kind);

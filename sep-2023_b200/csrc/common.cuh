@@ -73,12 +73,6 @@ struct SlotTab {
     const int *injRec;         // [slot][maxCon]
     const float *injCoef;      // [slot][maxCon]
     int maxInj, maxCon;
-    // receivers bucketed by the fused kernels' tiles (CSR): tilePtr[slot][nTiles+1], tileRec[slot][maxRec]
-    const int *tilePtr, *tileRec;
-    int nTiles, ntx;
-    // injection targets bucketed by tile INCLUDING its 2-cell halo (a target may sit in up to 4 tiles):
-    // tileInjPtr[slot][nTiles+1], tileInj[slot][4*maxInj] -> index into injCell/injField/injPtr
-    const int *tileInjPtr, *tileInj;
     // injection targets bucketed for the streaming kernels: per 120-column strip (4-column halo included, so a target
     // may sit in two strips) a row CSR  sInjPtr[slot][strip][nzA+1] into  sInj[slot][2*maxInj] -> target index
     const int *sInjPtr, *sInj;
@@ -151,6 +145,19 @@ __device__ __forceinline__ void ring_indices2(const Dims &d, int z, int x, int &
         if (i >= 0 && i < L) i1 = 2 * L * d.nzB + i * d.nxB + j;
         else if (ib >= 0 && ib < L) i1 = L * (2 * d.nzB + d.nxB) + ib * d.nxB + j;
     }
+}
+
+// cell inside the physical domain (the region the reverse-time sweep reconstructs, el_velocity.cu:88 / el_stress.cu:93)
+__device__ __forceinline__ bool interior(const Dims &d, int z, int x)
+{ return z >= d.nPml && z <= d.z1 && x >= d.nPml && x <= d.x1; }
+
+// does the inclusive cell rectangle [za_, zb_] x [xa_, xb_] touch the 5-wide boundary ring frame?
+__device__ __forceinline__ bool tile_touches_ring_ext(const Dims &d, int za_, int zb_, int xa_, int xb_)
+{
+    const int zlo = d.nPml - 2, zhi = d.z1 + 2, xlo = d.nPml - 2, xhi = d.x1 + 2;
+    const int za = max(za_, zlo), zb = min(zb_, zhi), xa = max(xa_, xlo), xb = min(xb_, xhi);
+    if (za > zb || xa > xb) return false;                                         // outside the frame's bounding box
+    return !(za >= zlo + 5 && zb <= zhi - 5 && xa >= xlo + 5 && xb <= xhi - 5);   // not entirely in the hole
 }
 
 }  // namespace sepfwi

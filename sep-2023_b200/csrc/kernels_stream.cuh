@@ -24,8 +24,6 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_base.cuh"
-#include "kernels_fused.cuh"      // tile_touches_ring_ext
-#include "kernels_fused_bwd.cuh"  // interior()
 
 namespace sepfwi {
 
@@ -1173,6 +1171,54 @@ __global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, 
     const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (RC_WARP_BYTES / 16);
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);
     else stream_rec_body<true>(a, sa, s, wk, lane, sw, sp);
+}
+
+// ================================================================================================
+// reverse-time step as ONE launch: reconstruction + imaging and the adjoint sweep are independent within a time step
+// (both read the adjoint state of buffer pa; one writes the forward buffer q^1 and the gradients, the other the adjoint
+// buffer pa^1), so their items share a launch.  CTA 2j+1 runs the reconstruction and CTA 2j+2 the adjoint sweep of the
+// SAME four (strip, chunk) items: the pair is dispatched together, and whichever of the two reads a row of the five
+// adjoint fields / five coefficient arrays second finds it in L2 -- on grids beyond the L2 that removes 40 of the
+// 164 bytes per cell the two separate launches move.  One launch per step also halves the launch / drain gaps on the
+// small grids.  grid: x = 1 + 2 ceil(nWork / SW_WPB), y = slot ; CTA 0 writes the stf gradient.
+constexpr size_t BW_ADJ_BYTES = AR_SMEM + (size_t)SW_WPB * 256 * sizeof(float);       // operand rings + the injection staging rows
+constexpr size_t BW_SMEM = RC_SMEM > BW_ADJ_BYTES ? RC_SMEM : BW_ADJ_BYTES;
+__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_bwd(const KArgs a, const StreamArgs sa)
+{
+    extern __shared__ __align__(16) float smem[];
+    pdl_launch_dependents();
+    const int s = blockIdx.y;
+    const Dims &d = a.d;
+    if (blockIdx.x == 0) {
+        pdl_wait();
+        if (threadIdx.x == 0) {      // source_grad, utilities.cu:719-730, from the adjoint state after step it+1
+            const float *src = slot_state(a, s) + (size_t)(sa.pa ? S_ADJ1 : S_ADJ) * d.fsz;
+            const size_t i = (size_t)a.t.zs[s] * d.ldx + a.t.xs[s];
+            a.gstf[(size_t)s * d.nSteps + sa.it] = -(src[(size_t)F_SZZ * d.fsz + i] + a.t.rxz[s] * src[(size_t)F_SXX * d.fsz + i]) * d.dt;
+        }
+        return;
+    }
+    const int b = (int)blockIdx.x - 1;
+    const int wi = (int)threadIdx.x >> 5;
+    const int wg = (b >> 1) * SW_WPB + wi;
+    if (wg >= sa.nWork) return;
+    const int4 wk = __ldg(sa.work + wg);
+    const int lane = threadIdx.x & 31;
+    const bool inner = (wk.w == 0 || sa.force == 1) && sa.force != 2;
+    if ((b & 1) == 0) {
+        const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + wi * RC_WARP_BYTES;
+        const float4 *sp = reinterpret_cast<const float4 *>(smem) + wi * (RC_WARP_BYTES / 16);
+        pdl_wait();
+        if (inner) stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);
+        else stream_rec_body<true>(a, sa, s, wk, lane, sw, sp);
+    } else {
+        const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + wi * AR_WARP_BYTES;
+        const float4 *sp = reinterpret_cast<const float4 *>(smem) + wi * (AR_WARP_BYTES / 16);
+        pdl_wait();
+        float *stage = smem + AR_SMEM / sizeof(float) + wi * 256;
+        if (inner) stream_adj_body<false>(a, sa, s, wk, lane, stage, sw, sp);
+        else stream_adj_body<true>(a, sa, s, wk, lane, stage, sw, sp);
+    }
 }
 
 }  // namespace sepfwi

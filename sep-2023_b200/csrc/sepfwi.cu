@@ -18,8 +18,6 @@
 #include "../../include/sepfwi.h"
 #include "common.cuh"
 #include "kernels_base.cuh"
-#include "kernels_fused.cuh"
-#include "kernels_fused_bwd.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_resident.cuh"
 
@@ -62,16 +60,22 @@ struct sepfwi_handle {
     size_t n_int = 0, n_flt = 0;
     SlotTab tab;
     // offsets (in elements) of the packed tables
-    size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_tilePtr, o_tileRec, o_tileInjPtr, o_tileInj, o_sInjPtr, o_sInj;
+    size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_sInjPtr, o_sInj;
     int nStrips = 0;
-    int ntx = 0, ntz = 0;
-    bool fused = false;    // tile kernels (kernels = 2); their backward half also serves kernels = 0 until the streaming one lands
-    bool stream = false;   // register-streaming kernels (kernels = 0)
+    bool stream = false;   // register-streaming kernels (kernels = 0 / 3); otherwise the unfused baseline kernels
+    bool merge_bwd = true; // reverse-time step as ONE launch: reconstruction and adjoint items of the same (strip, chunk) side by side
     int nSM = 148;
     size_t smem_optin = 0; // largest opt-in dynamic shared memory per block on this device
     bool pdl = true;       // programmatic dependent launch inside the time loops (SEPFWI_PDL=0 disables)
-    int4 *work[3] = {nullptr, nullptr, nullptr};   // work lists of the streaming kernels (device): forward, reconstruction, adjoint
-    size_t work_cap[3] = {0, 0, 0};
+    int warps_per_sm = SW_MINB * SW_WPB;   // resident warps per SM of the streaming kernels (register-bound)
+    // tuning / debugging knobs, read from the environment ONCE at creation (never inside a launch path):
+    // SEPFWI_LZ / SEPFWI_LZE chunk heights, SEPFWI_FORCE 1/2 force the interior / edge code path (timing only),
+    // SEPFWI_PLAN_DEBUG prints the plans, SEPFWI_RES_DEBUG the resident kernel's timing switches
+    int tune_lz = 0, tune_lze = 0, tune_force = 0, res_dbg = 0, res_forced_rpt = 0;
+    bool plan_debug = false, res_fake_refuse = false;
+    bool res_attr_done[16] = {false};      // cudaFuncSetAttribute issued for k_resident_fwd<RPT> on this handle's device
+    int4 *work[4] = {nullptr, nullptr, nullptr, nullptr};   // work lists of the streaming kernels (device): forward, reconstruction, adjoint, merged backward
+    size_t work_cap[4] = {0, 0, 0, 0};
     size_t o_amp, o_rxz, o_w, o_injCoef;
     bool use_w = false;
     // shared-memory-resident forward loop (kernels_resident.cuh): used when the tiles of a shot fit the SMs
@@ -90,6 +94,13 @@ struct sepfwi_handle {
     float courant = 0.f;
     bool have_model = false;
     long long launches = 0;
+    double *hj = nullptr; float *hg = nullptr;       // pinned staging: per-shot misfits, stf gradients
+    size_t hj_cap = 0, hg_cap = 0;
+    double last_misfit = 0.0;                        // misfit of the last sepfwi_gradient call in double precision
+    uint64_t staged_sig = 0;                         // signature of the batch the device slot tables hold (0: none)
+    uint64_t plan_sig[4] = {0, 0, 0, 0};             // ... and of the work lists (forward, reconstruction, adjoint, merged backward)
+    StreamArgs plan_sa[4];
+    int4 *work_host[4] = {nullptr, nullptr, nullptr, nullptr};    // pinned mirrors of the work lists
     cudaEvent_t ev[4];
     float fwd_ms = 0.f, bwd_ms = 0.f;
     static const int NBLK_RES = 64;
@@ -103,11 +114,11 @@ struct sepfwi_handle {
 };
 
 static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
-                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "fused_fwd", "fused_recon", "fused_adj", "stream_fwd", "stream_recon", "stream_adj", "resident_fwd"};
+                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "stream_fwd", "stream_recon", "stream_adj", "stream_bwd", "resident_fwd"};
 
 // Launch with programmatic stream serialization (the kernels call griddepcontrol.launch_dependents / .wait themselves).
 template <typename... KA, typename... A>
-static void launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, A... args)
+static cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, A... args)
 {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -116,7 +127,7 @@ static void launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, args...);
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 // launch `stmt` and, in profile mode, bracket it with an event pair
@@ -271,7 +282,7 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
                    h->dense[0], h->dense[1], h->dense[2], h->t_flt};
     for (float *q : fp) if (q) cudaFree(q);
     if (h->maxcp) cudaFree(h->maxcp);
-    for (int k = 0; k < 3; k++) if (h->work[k]) cudaFree(h->work[k]);
+    for (int k = 0; k < 4; k++) { if (h->work[k]) cudaFree(h->work[k]); if (h->work_host[k]) cudaFreeHost(h->work_host[k]); }
     if (h->partial) cudaFree(h->partial);
     if (h->misfit) cudaFree(h->misfit);
     if (h->t_int) cudaFree(h->t_int);
@@ -281,6 +292,8 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
     if (h->res_ring) cudaFree(h->res_ring);
     if (h->res_host) cudaFreeHost(h->res_host);
     if (h->res_errh) cudaFreeHost(h->res_errh);
+    if (h->hj) cudaFreeHost(h->hj);
+    if (h->hg) cudaFreeHost(h->hg);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return 0;
@@ -304,6 +317,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     if (rc) { delete h; return rc; }
     h->B = std::max(1, pp->max_batch);
     h->d.nTrace = h->sponge ? NTRACE : 4;
+    if (pp->kernels != 0 && pp->kernels != 1 && pp->kernels != 3) { delete h; return fail(SEPFWI_EINVAL, "kernels must be 0 (default), 1 (unfused baseline) or 3 (streaming only)"); }
     if (h->sponge && pp->with_adjoint) { delete h; return fail(SEPFWI_EINVAL, "the sponge flavour is forward-only (the reference has no adjoint for it)"); }
     const Dims &d = h->d;
     const int B = h->B;
@@ -346,25 +360,27 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     h->o_zrec = takei((size_t)B * d.maxRec); h->o_xrec = takei((size_t)B * d.maxRec);
     h->o_injN = takei(B); h->o_injCell = takei((size_t)B * maxInj); h->o_injField = takei((size_t)B * maxInj);
     h->o_injPtr = takei((size_t)B * (maxInj + 1)); h->o_injRec = takei((size_t)B * maxCon);
-    h->ntx = (d.nx + FTX - 1) / FTX; h->ntz = (d.nzA + FTZ - 1) / FTZ;
-    h->o_tilePtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileRec = takei((size_t)B * d.maxRec);
-    h->o_tileInjPtr = takei((size_t)B * (h->ntx * h->ntz + 1)); h->o_tileInj = takei((size_t)B * 4 * maxInj);
     h->nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
     h->o_sInjPtr = takei((size_t)B * h->nStrips * (d.nzA + 1)); h->o_sInj = takei((size_t)B * 2 * maxInj);
     h->n_int = oi;
     h->stream = !h->sponge && (pp->kernels == 0 || pp->kernels == 3);
     if (const char *e = getenv("SEPFWI_PDL")) h->pdl = atoi(e) != 0;
-    h->fused = !h->sponge && (pp->kernels == 0 || pp->kernels == 2 || pp->kernels == 3);
+    if (const char *e = getenv("SEPFWI_LZ")) h->tune_lz = atoi(e);
+    if (const char *e = getenv("SEPFWI_LZE")) h->tune_lze = atoi(e);
+    if (const char *e = getenv("SEPFWI_FORCE")) h->tune_force = atoi(e);
+    if (const char *e = getenv("SEPFWI_RES_DEBUG")) h->res_dbg = atoi(e);
+    if (const char *e = getenv("SEPFWI_RESIDENT_RPT")) h->res_forced_rpt = atoi(e);
+    h->plan_debug = getenv("SEPFWI_PLAN_DEBUG") != nullptr;
+    h->res_fake_refuse = getenv("SEPFWI_RES_FAKE_REFUSE") != nullptr;
+    if (const char *e = getenv("SEPFWI_MERGE_BWD")) h->merge_bwd = atoi(e) != 0;
     {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
         h->nSM = prop.multiProcessorCount;
         h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     }
-    if (h->fused) {
-        CU(cudaFuncSetAttribute(k_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-        CU(cudaFuncSetAttribute(k_fused_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
-        CU(cudaFuncSetAttribute(k_fused_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
+    if (h->stream) {
+        CU(cudaFuncSetAttribute(k_stream_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM));
         CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
         CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
         CU(cudaFuncSetAttribute(k_stream_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AR_SMEM));
@@ -409,8 +425,6 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     t.injPtr = h->t_int + h->o_injPtr; t.injRec = h->t_int + h->o_injRec;
     t.amp = h->t_flt + h->o_amp; t.rxz = h->t_flt + h->o_rxz; t.w = h->t_flt + h->o_w; t.injCoef = h->t_flt + h->o_injCoef;
     t.maxInj = maxInj; t.maxCon = maxCon;
-    t.tilePtr = h->t_int + h->o_tilePtr; t.tileRec = h->t_int + h->o_tileRec; t.nTiles = h->ntx * h->ntz; t.ntx = h->ntx;
-    t.tileInjPtr = h->t_int + h->o_tileInjPtr; t.tileInj = h->t_int + h->o_tileInj;
     t.sInjPtr = h->t_int + h->o_sInjPtr; t.sInj = h->t_int + h->o_sInj; t.nStrips = h->nStrips;
 
     // CPML profiles / sponge
@@ -530,36 +544,67 @@ extern "C" int sepfwi_courant(sepfwi_handle *h, float *c)
 // Per-batch host staging of the slot tables.
 struct InjEntry { int field, cell, rec; float coef; };
 
+// 64-bit mix of a byte range (word-wise; only used to recognise "the same shots as last time")
+static uint64_t hash_bytes(uint64_t hsh, const void *p, size_t n)
+{
+    const unsigned char *b = (const unsigned char *)p;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; memcpy(&w, b + i, 8); hsh = (hsh ^ w) * 0x9E3779B97F4A7C15ull; hsh ^= hsh >> 29; }
+    uint64_t w = 0;
+    if (i < n) memcpy(&w, b + i, n - i);
+    hsh = (hsh ^ w ^ (uint64_t)n) * 0xC2B2AE3D27D4EB4Full; hsh ^= hsh >> 32;
+    return hsh;
+}
+
+static uint64_t batch_signature(const sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool need_inject)
+{
+    uint64_t g = 0x5EF0F1ull + (uint64_t)nb * 131 + (need_inject ? 7 : 0);
+    for (int s = 0; s < nb; s++) {
+        const sepfwi_shot &sh = shots[s];
+        const int hd[3] = {sh.zs, sh.xs, sh.nrec};
+        g = hash_bytes(g, hd, sizeof(hd));
+        g = hash_bytes(g, &sh.src_rxz, sizeof(float));
+        if (sh.nrec > 0 && sh.zrec && sh.xrec) { g = hash_bytes(g, sh.zrec, (size_t)sh.nrec * 4); g = hash_bytes(g, sh.xrec, (size_t)sh.nrec * 4); }
+        if (sh.stf) g = hash_bytes(g, sh.stf, (size_t)h->d.nSteps * 4);
+        if (sh.weights) g = hash_bytes(g, sh.weights, (size_t)sh.nrec * 12);
+        else g = hash_bytes(g, "nw", 2);
+    }
+    return g | 1ull;      // never 0 (0 = nothing staged)
+}
+
+// Fills the pinned mirrors and uploads them -- unless the device tables already hold exactly this batch (an inversion calls
+// with the same shots on every evaluation: then nothing is recomputed, allocated or copied).
 static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool need_inject, cudaStream_t st)
 {
     const Dims &d = h->d;
     const int maxCon = h->tab.maxCon, maxInj = h->tab.maxInj;
-    h->use_w = false;
-    for (int s = 0; s < nb; s++) if (shots[s].weights) h->use_w = true;
     for (int s = 0; s < nb; s++) {
         const sepfwi_shot &sh = shots[s];
         if (sh.nrec < 0 || sh.nrec > d.maxRec) return fail(SEPFWI_EINVAL, "shot %d: nrec %d exceeds max_nrec %d", s, sh.nrec, d.maxRec);
         if (sh.zs < 2 || sh.zs > d.nzA - 3 || sh.xs < 2 || sh.xs > d.nx - 3) return fail(SEPFWI_EINVAL, "shot %d: source (%d,%d) outside the active grid", s, sh.zs, sh.xs);
         if (!sh.stf) return fail(SEPFWI_EINVAL, "shot %d: null stf", s);
         if (sh.nrec > 0 && (!sh.zrec || !sh.xrec)) return fail(SEPFWI_EINVAL, "shot %d: null receiver arrays", s);
-        h->h_int[h->o_zs + s] = sh.zs; h->h_int[h->o_xs + s] = sh.xs; h->h_int[h->o_nrec + s] = sh.nrec;
         for (int r = 0; r < sh.nrec; r++) {
             const int z = sh.zrec[r], x = sh.xrec[r];
             if (z < 1 || z > d.nzA - 2 || x < 1 || x > d.nx - 2) return fail(SEPFWI_EINVAL, "shot %d: receiver %d at (%d,%d) outside the grid", s, r, z, x);
-            h->h_int[h->o_zrec + (size_t)s * d.maxRec + r] = z;
-            h->h_int[h->o_xrec + (size_t)s * d.maxRec + r] = x;
+        }
+    }
+    const uint64_t sig = batch_signature(h, nb, shots, need_inject);
+    if (sig == h->staged_sig) return 0;
+    // the previous batch's upload may still be reading the pinned mirrors
+    if (h->staged_sig) CU(cudaStreamSynchronize(st));
+    h->staged_sig = 0;
+    h->use_w = false;
+    for (int s = 0; s < nb; s++) if (shots[s].weights) h->use_w = true;
+    for (int s = 0; s < nb; s++) {
+        const sepfwi_shot &sh = shots[s];
+        h->h_int[h->o_zs + s] = sh.zs; h->h_int[h->o_xs + s] = sh.xs; h->h_int[h->o_nrec + s] = sh.nrec;
+        for (int r = 0; r < sh.nrec; r++) {
+            h->h_int[h->o_zrec + (size_t)s * d.maxRec + r] = sh.zrec[r];
+            h->h_int[h->o_xrec + (size_t)s * d.maxRec + r] = sh.xrec[r];
             float *w = h->h_flt + h->o_w + ((size_t)s * d.maxRec + r) * 3;
             if (sh.weights) { w[0] = sh.weights[3 * r]; w[1] = sh.weights[3 * r + 1]; w[2] = sh.weights[3 * r + 2]; }
             else { w[0] = h->p.fiber == SEPFWI_FIBER_EXX ? 1.f : 0.f; w[1] = h->p.fiber == SEPFWI_FIBER_EZZ ? 1.f : 0.f; w[2] = 0.f; }
-        }
-        {   // receivers bucketed by fused-kernel tile (counting sort, stable in receiver index)
-            const int nT = h->ntx * h->ntz;
-            int *tp = h->h_int + h->o_tilePtr + (size_t)s * (nT + 1), *trc = h->h_int + h->o_tileRec + (size_t)s * d.maxRec;
-            std::fill(tp, tp + nT + 1, 0);
-            for (int r = 0; r < sh.nrec; r++) tp[(sh.zrec[r] / FTZ) * h->ntx + sh.xrec[r] / FTX + 1]++;
-            for (int t = 0; t < nT; t++) tp[t + 1] += tp[t];
-            std::vector<int> cur(tp, tp + nT);
-            for (int r = 0; r < sh.nrec; r++) trc[cur[(sh.zrec[r] / FTZ) * h->ntx + sh.xrec[r] / FTX]++] = r;
         }
         // source amplitude per step
         float *amp = h->h_flt + h->o_amp + (size_t)s * d.nSteps;
@@ -604,25 +649,7 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
             }
             ptr[nt] = (int)v.size();
             h->h_int[h->o_injN + s] = nt;
-            // bucket the targets by fused-kernel tile, halo of 2 included
-            const int nT = h->ntx * h->ntz;
-            int *tp = h->h_int + h->o_tileInjPtr + (size_t)s * (nT + 1), *tl = h->h_int + h->o_tileInj + (size_t)s * 4 * maxInj;
-            std::fill(tp, tp + nT + 1, 0);
-            auto for_tiles = [&](int m, auto &&fn) {
-                const int z = cell[m] / d.ldx, x = cell[m] % d.ldx;
-                const int tz0 = std::max(0, (z - 2) / FTZ), tz1 = std::min(h->ntz - 1, (z + 2) / FTZ);
-                const int tx0 = std::max(0, (x - 2) / FTX), tx1 = std::min(h->ntx - 1, (x + 2) / FTX);
-                for (int tz = tz0; tz <= tz1; tz++)
-                    for (int tx = tx0; tx <= tx1; tx++) {
-                        const int zz0 = tz * FTZ, xx0 = tx * FTX;
-                        if (z >= zz0 - 2 && z <= zz0 + FTZ + 1 && x >= xx0 - 2 && x <= xx0 + FTX + 1) fn(tz * h->ntx + tx);
-                    }
-            };
-            for (int m = 0; m < nt; m++) for_tiles(m, [&](int t) { tp[t + 1]++; });
-            for (int t = 0; t < nT; t++) tp[t + 1] += tp[t];
-            std::vector<int> cur(tp, tp + nT);
-            for (int m = 0; m < nt; m++) for_tiles(m, [&](int t) { tl[cur[t]++] = m; });
-            // ... and by streaming strip (columns [120 k - 4, 120 k + 124)) and row
+            // bucket the targets by streaming strip (columns [120 k - 4, 120 k + 124)) and row
             const int nS = h->nStrips, nR = d.nzA + 1;
             int *sp = h->h_int + h->o_sInjPtr + (size_t)s * nS * nR, *sl = h->h_int + h->o_sInj + (size_t)s * 2 * maxInj;
             std::fill(sp, sp + (size_t)nS * nR, 0);
@@ -642,17 +669,16 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
             std::vector<int> cur2((size_t)nS * d.nzA);
             for (int k = 0; k < nS; k++) for (int z = 0; z < d.nzA; z++) cur2[(size_t)k * d.nzA + z] = sp[(size_t)k * nR + z];
             for (int m = 0; m < nt; m++) for_strips(m, [&](int k, int z) { sl[cur2[(size_t)k * d.nzA + z]++] = m; });
-        }
+        } else h->h_int[h->o_injN + s] = 0;
     }
     for (int s = nb; s < h->B; s++) {
         h->h_int[h->o_nrec + s] = 0; h->h_int[h->o_injN + s] = 0;
-        const int nT = h->ntx * h->ntz;
-        std::fill(h->h_int + h->o_tilePtr + (size_t)s * (nT + 1), h->h_int + h->o_tilePtr + (size_t)(s + 1) * (nT + 1), 0);
-        std::fill(h->h_int + h->o_tileInjPtr + (size_t)s * (nT + 1), h->h_int + h->o_tileInjPtr + (size_t)(s + 1) * (nT + 1), 0);
         std::fill(h->h_int + h->o_sInjPtr + (size_t)s * h->nStrips * (d.nzA + 1), h->h_int + h->o_sInjPtr + (size_t)(s + 1) * h->nStrips * (d.nzA + 1), 0);
     }
     CU(cudaMemcpyAsync(h->t_int, h->h_int, h->n_int * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->t_flt, h->h_flt, h->n_flt * sizeof(float), cudaMemcpyHostToDevice, st));
+    h->staged_sig = sig;
+    for (int k = 0; k < 4; k++) h->plan_sig[k] = 0;      // the adjoint plan looks at the staged injection tables
     return 0;
 }
 
@@ -668,16 +694,22 @@ static int max_nrec(int nb, const sepfwi_shot *shots)
 //     CPML memory variables, no look-ahead): they get shorter chunks and are listed first so they never form the tail;
 //   * interior chunks are Lz rows with (Lz + 4) a multiple of the 6-row unroll, Lz chosen so that the item count fills whole
 //     waves of nSM x 8 resident warps (2 CTAs x 4 warps at 255 registers).  SEPFWI_LZ / SEPFWI_LZE override the two heights.
-static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 adj*/, StreamArgs &sa, std::vector<int4> *items_out = nullptr)
+static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 adj, 3 merged recon + adj*/, StreamArgs &sa, cudaStream_t st,
+                       std::vector<int4> *items_out = nullptr)
 {
     const Dims &d = h->d;
+    // same batch, same kernel: the device work list is still valid
+    const uint64_t want = h->staged_sig ? (h->staged_sig ^ ((uint64_t)nb << 48)) | 1ull : 0;
+    if (!items_out && want && h->plan_sig[which] == want) { sa = h->plan_sa[which]; return 0; }
     memset(&sa, 0, sizeof(sa));
+    const int model = which == 3 ? 2 : which;            // the merged launch is planned with the adjoint sweep's costs ...
+    const double mult = which == 3 ? 2.0 : 1.0;           // ... and carries two warps per item
     const int nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
     // interior rows [zi0, zi1) / strips: the adjoint sweep keeps CPML memory on strips nPml + 2 wide (el_stress_adj.cu:67-72),
     // a warp recomputes a 2-cell halo, and the reverse sweep restores a ring that reaches 3 cells into the interior:
     // the branch-free variants need a margin of nPml + 5
     const int zi0 = d.nPml + 5, zi1 = d.nzA - d.nPml - 5;
-    const double conc = (double)h->nSM * 2 * SW_WPB;
+    const double conc = (double)h->nSM * h->warps_per_sm;
     auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 3 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 4; };
     int nInnerStrips = 0;
     for (int sx = 0; sx < nStrips; sx++) nInnerStrips += strip_inner(sx) ? 1 : 0;
@@ -686,7 +718,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     // measured cost of an edge row relative to an interior row: in throughput (many waves, HBM-bound) and in latency
     // (a lone warp per scheduler: shorter look-ahead, register moves); the CPML rows of the adjoint sweep are the expensive ones
     static const double edge_thr[3] = {1.15, 1.1, 1.8}, edge_lat[3] = {2.0, 1.6, 2.5};
-    const double edge_cost = edge_thr[which], edge_latc = edge_lat[which];
+    const double edge_cost = edge_thr[model], edge_latc = edge_lat[model];
     auto counts = [&](int Lz, int Le, double &n_in, double &n_ed) {
         const int nch = (zi1 - zi0 + Lz - 1) / Lz, nche = (zi1 - zi0 + Le - 1) / Le, ntb = 2 * ((zi0 + Le - 1) / Le);
         n_in = (double)nInnerStrips * nch;
@@ -700,22 +732,22 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
             double n_in, n_ed;
             counts(Lz, le, n_in, n_ed);
             const double it_i = 6 * ((Lz + 4 + 5) / 6) + 3.0, it_e = (le + 4 + 3.0) * edge_cost;   // rows per item (+3: prologue)
-            const double work = (n_in * it_i + n_ed * it_e) * nb / conc, longest = std::max(it_i, (le + 4 + 3.0) * edge_latc);
+            const double work = (n_in * it_i + n_ed * it_e) * nb * mult / conc, longest = std::max(it_i, (le + 4 + 3.0) * edge_latc);
             // one wave or less: the longest item is the time; many waves: throughput plus half an item of tail
             double c = std::max(longest, work + 0.5 * longest);
             // a few waves: whole waves of latency-bound items (measured: 19 shots of the 192 x 265 grid at 63 items per shot are
             // 1197 items = 2 waves and 91 us, at 48 items per shot 1 wave and 64 us).  The reconstruction kernel's items outside
             // the interior + ring return at once and do not occupy a slot.
-            const double live = which == 1 ? std::min(1.0, (double)(d.nzA - 2 * d.nPml + 4) / d.nzA) : 1.0;
-            const double waves = ceil((n_in + n_ed) * nb * live / conc);
+            const double live = model == 1 ? std::min(1.0, (double)(d.nzA - 2 * d.nPml + 4) / d.nzA) : 1.0;
+            const double waves = ceil((n_in + n_ed) * nb * mult * live / conc);
             if (waves <= 3.0 && n_in + n_ed > 0)
                 c = std::max(c, waves * (n_in * it_i + n_ed * (le + 4 + 3.0) * edge_latc) / (n_in + n_ed));
             if (c < bestc - 1e-9) { bestc = c; best = Lz; Le = le; }
         }
-    if (const char *e = getenv("SEPFWI_LZ")) { const int v = atoi(e); if (v >= 2) best = v; }
-    if (const char *e = getenv("SEPFWI_LZE")) { const int v = atoi(e); if (v >= 2) Le = v; }
-    if (const char *e = getenv("SEPFWI_FORCE")) sa.force = atoi(e);
-    if (getenv("SEPFWI_PLAN_DEBUG")) fprintf(stderr, "stream_plan[%d]: nb %d Lz %d Le %d (%.0f) cost %.1f\n", which, nb, best, Le, 0.0, bestc);
+    if (h->tune_lz >= 2) best = h->tune_lz;
+    if (h->tune_lze >= 2) Le = h->tune_lze;
+    sa.force = h->tune_force;
+    if (h->plan_debug) fprintf(stderr, "stream_plan[%d]: nb %d Lz %d Le %d cost %.1f\n", which, nb, best, Le, bestc);
     std::vector<int4> edge, inner;
     auto split = [&](int z0, int z1, int L, int sx, bool is_edge) {
         const int n = (z1 - z0 + L - 1) / L;
@@ -727,7 +759,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     // adjoint sweep: strips that hold residual-injection targets (a vertical fiber puts targets on every row of one strip) are
     // slower per row (staging + dependent table loads): half-height chunks, listed first, so they do not form the tail
     std::vector<char> heavy(nStrips, 0);
-    if (which == 2 && h->h_int)
+    if (model == 2 && h->h_int)
         for (int s_ = 0; s_ < nb; s_++)
             for (int sx = 0; sx < nStrips; sx++) {
                 const int *sp = h->h_int + h->o_sInjPtr + ((size_t)s_ * h->nStrips + sx) * (d.nzA + 1);
@@ -747,13 +779,20 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     edge.insert(edge.end(), inner.begin(), inner.end());
     if (items_out) { *items_out = edge; return 0; }      // host-only planning (sepfwi_plan_stream): nothing is uploaded
     if (edge.size() > h->work_cap[which]) {
+        // kernels of earlier calls may still read the old list
+        CU(cudaStreamSynchronize(st));
         if (h->work[which]) cudaFree(h->work[which]);
-        h->work[which] = nullptr; h->work_cap[which] = 0;
-        CU(cudaMalloc((void **)&h->work[which], edge.size() * sizeof(int4)));
-        h->work_cap[which] = edge.size();
-    }
-    CU(cudaMemcpy(h->work[which], edge.data(), edge.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        if (h->work_host[which]) cudaFreeHost(h->work_host[which]);
+        h->work[which] = nullptr; h->work_host[which] = nullptr; h->work_cap[which] = 0;
+        const size_t cap = edge.size() + edge.size() / 4 + 64;
+        CU(cudaMalloc((void **)&h->work[which], cap * sizeof(int4)));
+        CU(cudaMallocHost((void **)&h->work_host[which], cap * sizeof(int4)));
+        h->work_cap[which] = cap;
+    } else if (h->plan_sig[which]) CU(cudaStreamSynchronize(st));      // the pinned mirror may still be in flight / the list in use
+    memcpy(h->work_host[which], edge.data(), edge.size() * sizeof(int4));
+    CU(cudaMemcpyAsync(h->work[which], h->work_host[which], edge.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
     sa.work = h->work[which]; sa.nWork = (int)edge.size();
+    h->plan_sa[which] = sa; h->plan_sig[which] = want;
     return 0;
 }
 
@@ -765,15 +804,13 @@ static const int RES_UNAVAILABLE = 12345;   // run_resident: the cooperative lau
 static int resident_check(sepfwi_handle *h);
 
 template <int RPT>
-static cudaError_t launch_resident(dim3 grid, const KArgs &a, const ResArgs &ra, cudaStream_t st)
+static cudaError_t launch_resident(sepfwi_handle *h, dim3 grid, const KArgs &a, const ResArgs &ra, cudaStream_t st)
 {
-    static bool attr_done[64] = {false};      // per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_done[dev]) {
+    static_assert(RPT < 16, "res_attr_done is indexed by RPT");
+    if (!h->res_attr_done[RPT]) {      // per handle (one handle = one device, one thread at a time): no shared mutable state
         cudaError_t e = cudaFuncSetAttribute(k_resident_fwd<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(RPT));
         if (e != cudaSuccess) return e;
-        attr_done[dev] = true;
+        h->res_attr_done[RPT] = true;
     }
     void *args[2] = {(void *)&a, (void *)&ra};
     return cudaLaunchCooperativeKernel((void *)k_resident_fwd<RPT>, grid, dim3(RS_NT), args, rs_smem_bytes(RPT), st);
@@ -793,8 +830,7 @@ static ResPlan resident_plan(const sepfwi_handle *h, int nb)
         const int lo = std::max(t * RS_OW - 4, 0), hi = std::min(t * RS_OW + RS_EW - 5, d.nx - 1);
         if (lo < d.nPml && hi > d.nx - d.nPml - 1) return best;
     }
-    int forced = 0;
-    if (const char *e = getenv("SEPFWI_RESIDENT_RPT")) forced = atoi(e);
+    const int forced = h->res_forced_rpt;
     double bestc = 1e300;
     for (int rpt : k_res_rpts) {
         if (forced && rpt != forced) continue;
@@ -821,7 +857,7 @@ static ResPlan resident_plan(const sepfwi_handle *h, int nb)
     const double inner = (double)std::max(0, d.nzA - 2 * (d.nPml + 5)) * std::max(0, d.nx - 2 * (d.nPml + 5));
     const double t_stream = std::max(10.0 + 20.0 * (cells - inner) / cells, 1e6 * nb * (inner / 7.0e10 + (cells - inner) / 2.5e10));
     if (best.rpt && !forced && bestc >= t_stream) best = ResPlan();
-    if (getenv("SEPFWI_PLAN_DEBUG")) fprintf(stderr, "resident_plan: nb %d -> rpt %d, %d x %d tiles of %d x %d, %d shots per launch\n", nb, best.rpt, best.ntx, best.ntz, best.orows, RS_OW, best.per_launch);
+    if (h->plan_debug) fprintf(stderr, "resident_plan: nb %d -> rpt %d, %d x %d tiles of %d x %d, %d shots per launch\n", nb, best.rpt, best.ntx, best.ntz, best.orows, RS_OW, best.per_launch);
     return best;
 }
 
@@ -849,7 +885,7 @@ extern "C" int sepfwi_plan_resident(const sepfwi_params *pp, int nshots, int nsm
 // *n receives the number of items the plan has (may exceed cap).
 extern "C" int sepfwi_plan_stream(const sepfwi_params *pp, int nshots, int nsm, int which, int *items, int cap, int *n)
 {
-    if (!pp || !n || nshots < 1 || nsm < 1 || which < 0 || which > 2 || (cap > 0 && !items)) return fail(SEPFWI_EINVAL, "bad argument");
+    if (!pp || !n || nshots < 1 || nsm < 1 || which < 0 || which > 3 || (cap > 0 && !items)) return fail(SEPFWI_EINVAL, "bad argument");
     sepfwi_handle h;
     h.p = *pp;
     int rc = fill_dims(*pp, h.d);
@@ -857,7 +893,7 @@ extern "C" int sepfwi_plan_stream(const sepfwi_params *pp, int nshots, int nsm, 
     h.nSM = nsm;
     StreamArgs sa;
     std::vector<int4> v;
-    rc = stream_plan(&h, nshots, which, sa, &v);
+    rc = stream_plan(&h, nshots, which, sa, nullptr, &v);
     if (rc) return rc;
     *n = (int)v.size();
     for (int i = 0; i < (int)v.size() && i < cap; i++) { items[4 * i] = v[i].x; items[4 * i + 1] = v[i].y; items[4 * i + 2] = v[i].z; items[4 * i + 3] = v[i].w; }
@@ -936,26 +972,26 @@ static int run_resident(sepfwi_handle *h, const ResPlan &pl, int s0, int n, int 
     ResArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.ntx = pl.ntx; ra.ntz = pl.ntz; ra.orows = pl.orows; ra.slot0 = s0; ra.mask = mask; ra.fiber = h->p.fiber; ra.save_ring = save_ring ? 1 : 0;
-    if (const char *e = getenv("SEPFWI_RES_DEBUG")) ra.dbg = atoi(e);
+    ra.dbg = h->res_dbg;
     ra.flags = h->res_dev + h->ro_flags; ra.err = h->res_dev + h->ro_err;
     ra.tilePtr = h->res_dev + h->ro_tptr; ra.tileRec = h->res_dev + h->ro_trec;
     ra.ringPtr = h->res_dev + h->ro_rptr; ra.ringEnt = h->res_ring;
     const dim3 grid(nT, n);
     cudaError_t e = cudaErrorInvalidValue;
-    if (getenv("SEPFWI_RES_FAKE_REFUSE")) e = cudaErrorCooperativeLaunchTooLarge;     // test hook for the fallback below
+    if (h->res_fake_refuse) e = cudaErrorCooperativeLaunchTooLarge;     // test hook for the fallback below
     else
     switch (pl.rpt) {
-    case 3: e = launch_resident<3>(grid, a, ra, st); break;
-    case 4: e = launch_resident<4>(grid, a, ra, st); break;
-    case 5: e = launch_resident<5>(grid, a, ra, st); break;
-    case 6: e = launch_resident<6>(grid, a, ra, st); break;
-    case 7: e = launch_resident<7>(grid, a, ra, st); break;
-    case 8: e = launch_resident<8>(grid, a, ra, st); break;
-    case 9: e = launch_resident<9>(grid, a, ra, st); break;
-    case 10: e = launch_resident<10>(grid, a, ra, st); break;
-    case 11: e = launch_resident<11>(grid, a, ra, st); break;
-    case 12: e = launch_resident<12>(grid, a, ra, st); break;
-    case 13: e = launch_resident<13>(grid, a, ra, st); break;
+    case 3: e = launch_resident<3>(h, grid, a, ra, st); break;
+    case 4: e = launch_resident<4>(h, grid, a, ra, st); break;
+    case 5: e = launch_resident<5>(h, grid, a, ra, st); break;
+    case 6: e = launch_resident<6>(h, grid, a, ra, st); break;
+    case 7: e = launch_resident<7>(h, grid, a, ra, st); break;
+    case 8: e = launch_resident<8>(h, grid, a, ra, st); break;
+    case 9: e = launch_resident<9>(h, grid, a, ra, st); break;
+    case 10: e = launch_resident<10>(h, grid, a, ra, st); break;
+    case 11: e = launch_resident<11>(h, grid, a, ra, st); break;
+    case 12: e = launch_resident<12>(h, grid, a, ra, st); break;
+    case 13: e = launch_resident<13>(h, grid, a, ra, st); break;
     }
     if (e != cudaSuccess) {
         // the device cannot co-schedule the tiles (fewer SMs than planned for, a partitioned GPU, ...): not an error of the
@@ -1003,7 +1039,7 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
     if (rpl.rpt) {
     } else if (h->stream) {
         StreamArgs sa;
-        int rc = stream_plan(h, nb, 0, sa);
+        int rc = stream_plan(h, nb, 0, sa, st);
         if (rc) return rc;
         sa.fiber = h->p.fiber; sa.save_ring = save_ring ? 1 : 0; sa.nrecMax = mrec;
         const int items = (mrec > 0 ? mrec : 0) + (save_ring ? d.ringLen : 0);
@@ -1012,17 +1048,9 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
         for (int it = 0; it <= d.nSteps - 2; it++) {
             const bool pr = it < h->prof_steps;
             sa.it = it; sa.mask = (it >= 1 && mrec > 0) ? mask : 0;
-            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), FR_SMEM, st, h->pdl, a, sa)));
-        }
-        const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state
-        if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, false, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, d.nSteps - 1, mask, h->p.fiber, par)));
-    } else if (h->fused) {
-        dim3 fgrd(h->ntx, h->ntz, nb);
-        for (int it = 0; it <= d.nSteps - 2; it++) {
-            const bool pr = it < h->prof_steps;
-            FusedFwdArgs fa;
-            fa.it = it; fa.mask = (it >= 1 && mrec > 0) ? mask : 0; fa.fiber = h->p.fiber; fa.save_ring = save_ring ? 1 : 0;
-            LAUNCH(h, SEPFWI_K_FUSED_FWD, pr, st, (k_fused_fwd<<<fgrd, F4_NT, F_SMEM, st>>>(a, fa)));
+            cudaError_t le = cudaSuccess;
+            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (le = launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), FR_SMEM, st, h->pdl, a, sa)));
+            CU(le);
         }
         const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state
         if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, false, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, d.nSteps - 1, mask, h->p.fiber, par)));
@@ -1121,29 +1149,31 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     const int rx = d.x1 + 2 - (d.nPml - 2) + 1, rz = d.z1 + 2 - (d.nPml - 2) + 1;
     dim3 rgrd((rx + BX - 1) / BX, (rz + BY - 1) / BY, nb);
     dim3 igrd((minj + 127) / 128, nb);
+    StreamArgs sa, sr, sm;
+    if (h->stream) {
+        int rc;
+        if (h->merge_bwd) { rc = stream_plan(h, nb, 3, sm, st); if (rc) return rc; }
+        else { rc = stream_plan(h, nb, 2, sa, st); if (rc) return rc; rc = stream_plan(h, nb, 1, sr, st); if (rc) return rc; }
+    }
     CU(cudaEventRecord(h->ev[2], st));
-    StreamArgs sa, sr;
-    if (h->stream) { int rc = stream_plan(h, nb, 2, sa); if (rc) return rc; rc = stream_plan(h, nb, 1, sr); if (rc) return rc; }
-    if (h->fused) {
-        dim3 agrd(h->ntx, h->ntz, nb);
-        dim3 sagrd(1 + (sa.nWork + SW_WPB - 1) / SW_WPB, nb);
-        const int xbase = (d.nPml - 2) & ~3;
-        dim3 cgrd((d.x1 + 2 - xbase) / FTX + 1, (d.z1 + 2 - (d.nPml - 2)) / FTZ + 1, nb);
+    if (h->stream) {
         int q = (d.nSteps - 1) & 1, pa = 0;     // forward state nSteps-1 sits in buffer q; adjoint starts in buffer 0
+        const int nctas = (sm.nWork + SW_WPB - 1) / SW_WPB;
         for (int it = d.nSteps - 2; it >= 0; it--) {
             const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
-            FusedBwdArgs fa;
-            fa.it = it; fa.q = q; fa.pa = pa;
-            if (h->stream && !getenv("SEPFWI_TILE_RECON")) {
+            cudaError_t le = cudaSuccess;
+            if (h->merge_bwd) {
+                // one launch: CTA 0 writes the stf gradient, then CTA pairs (reconstruction, adjoint) over the same items
+                sm.it = it; sm.q = q; sm.pa = pa;
+                LAUNCH(h, SEPFWI_K_STREAM_BWD, pr, st, (le = launch_pdl(k_stream_bwd, dim3(1 + 2 * nctas, nb), dim3(SW_NT), BW_SMEM, st, h->pdl, a, sm)));
+            } else {
                 sr.it = it; sr.q = q; sr.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (launch_pdl(k_stream_recon, dim3((sr.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM, st, h->pdl, a, sr)));
-            } else
-            LAUNCH(h, SEPFWI_K_FUSED_RECON, pr, st, (k_fused_recon<<<cgrd, F4_NT, R_SMEM, st>>>(a, fa)));
-            if (h->stream) {
+                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (le = launch_pdl(k_stream_recon, dim3((sr.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM, st, h->pdl, a, sr)));
+                CU(le);
                 sa.it = it; sa.q = q; sa.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (launch_pdl(k_stream_adj, sagrd, dim3(SW_NT), AR_SMEM, st, h->pdl, a, sa)));
-            } else
-            LAUNCH(h, SEPFWI_K_FUSED_ADJ, pr, st, (k_fused_adj<<<agrd, F4_NT, A_SMEM, st>>>(a, fa)));
+                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (le = launch_pdl(k_stream_adj, dim3(1 + (sa.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), AR_SMEM, st, h->pdl, a, sa)));
+            }
+            CU(le);
             q ^= 1; pa ^= 1;
         }
     } else
@@ -1160,6 +1190,24 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     return 0;
 }
 
+// Pinned staging for the small per-call results (per-shot misfit, stf gradients): grown on demand, never per call.
+static int ensure_result_staging(sepfwi_handle *h, size_t n_misfit, size_t n_gstf)
+{
+    if (n_misfit > h->hj_cap) {
+        if (h->hj) cudaFreeHost(h->hj);
+        h->hj = nullptr; h->hj_cap = 0;
+        CU(cudaMallocHost((void **)&h->hj, n_misfit * sizeof(double)));
+        h->hj_cap = n_misfit;
+    }
+    if (n_gstf > h->hg_cap) {
+        if (h->hg) cudaFreeHost(h->hg);
+        h->hg = nullptr; h->hg_cap = 0;
+        CU(cudaMallocHost((void **)&h->hg, n_gstf * sizeof(float)));
+        h->hg_cap = n_gstf;
+    }
+    return 0;
+}
+
 extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *shots, int with_adj,
                                float *misfit, float *glam, float *gmu, float *grho, int mem, void *stream)
 {
@@ -1173,13 +1221,15 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
     const Dims &d = h->d;
     const cudaMemcpyKind kin = mem == SEPFWI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     const cudaMemcpyKind kout = mem == SEPFWI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    int rc = ensure_result_staging(h, (size_t)nshots, with_adj ? (size_t)nshots * d.nSteps : 0);
+    if (rc) return rc;
     if (with_adj) CU(cudaMemsetAsync(h->grad, 0, (size_t)h->B * 3 * d.fsz * sizeof(float), st));
-    double J = 0.0;
     h->fwd_ms = 0.f; h->bwd_ms = 0.f;
     const size_t cs = (size_t)d.maxRec * d.nSteps;
+    const bool timing = h->prof_steps > 0 || nshots > h->B;      // several batches: the event pairs are reused, read them per batch
     for (int s0 = 0; s0 < nshots; s0 += h->B) {
         const int nb = std::min(h->B, nshots - s0);
-        int rc = stage_batch(h, nb, shots + s0, with_adj != 0, st);
+        rc = stage_batch(h, nb, shots + s0, with_adj != 0, st);
         if (rc) return rc;
         const int mrec = max_nrec(nb, shots + s0);
         rc = run_forward(h, nb, mrec, 1 << T_ETT, with_adj != 0, st);
@@ -1197,8 +1247,7 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
         k_sum_partials<<<1, 32 * ((nb + 31) / 32), 0, st>>>(h->partial, sepfwi_handle::NBLK_RES, h->misfit, nb);
         h->launches += 2;
         CU(cudaGetLastError());
-        std::vector<double> hj(nb);
-        CU(cudaMemcpyAsync(hj.data(), h->misfit, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->hj + s0, h->misfit, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
         for (int s = 0; s < nb; s++)
             if (shots[s0 + s].out[T_ETT] && shots[s0 + s].nrec > 0)
                 CU(cudaMemcpyAsync(shots[s0 + s].out[T_ETT], h->trace + ((size_t)s * d.nTrace + T_ETT) * cs,
@@ -1208,24 +1257,23 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
             for (int s = 0; s < nb; s++) minj = std::max(minj, h->h_int[h->o_injN + s]);
             rc = run_backward(h, nb, minj, st);
             if (rc) return rc;
+            // one asynchronous copy of the batch's stf gradients into pinned staging (handed out after the final sync)
+            CU(cudaMemcpyAsync(h->hg + (size_t)s0 * d.nSteps, h->gstf, (size_t)nb * d.nSteps * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
-        CU(cudaStreamSynchronize(st));
-        prof_collect(h);
-        rc = resident_check(h);
-        if (rc) return rc;
-        for (int s = 0; s < nb; s++) J += hj[s];
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-        h->fwd_ms += ms;
-        if (with_adj) {
-            CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
-            h->bwd_ms += ms;
-            for (int s = 0; s < nb; s++)
-                if (shots[s0 + s].gstf)
-                    CU(cudaMemcpy(shots[s0 + s].gstf, h->gstf + (size_t)s * d.nSteps, d.nSteps * sizeof(float), cudaMemcpyDeviceToHost));
+        if (timing || s0 + h->B >= nshots) {
+            // the last batch is followed by the gradient reduction below: no sync here unless timing needs the events
+            if (timing) {
+                CU(cudaStreamSynchronize(st));
+                prof_collect(h);
+                rc = resident_check(h);
+                if (rc) return rc;
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+                h->fwd_ms += ms;
+                if (with_adj) { CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->bwd_ms += ms; }
+            }
         }
     }
-    if (misfit) *misfit = (float)(0.5 * J);
     if (with_adj) {
         float *outs[3] = {glam, gmu, grho};
         dim3 blk(32, 8), grd((d.nx + 31) / 32, (d.nz + 7) / 8);
@@ -1237,8 +1285,25 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
                 CU(cudaMemcpyAsync(outs[k], dst, (size_t)d.nz * d.nx * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(st));
     }
+    // ONE synchronisation per call: the misfit is a host scalar of the C ABI, so the call cannot return earlier
+    CU(cudaStreamSynchronize(st));
+    if (!timing) {
+        prof_collect(h);
+        rc = resident_check(h);
+        if (rc) return rc;
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        h->fwd_ms = ms;
+        if (with_adj) { CU(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); h->bwd_ms = ms; }
+    }
+    double J = 0.0;
+    for (int s = 0; s < nshots; s++) J += h->hj[s];
+    if (misfit) *misfit = (float)(0.5 * J);
+    h->last_misfit = 0.5 * J;
+    if (with_adj)
+        for (int s = 0; s < nshots; s++)
+            if (shots[s].gstf) memcpy(shots[s].gstf, h->hg + (size_t)s * d.nSteps, (size_t)d.nSteps * sizeof(float));
     return 0;
 }
 

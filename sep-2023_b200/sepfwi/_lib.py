@@ -38,7 +38,7 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
            "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots", "sepfwi_plan_resident", "sepfwi_plan_stream"]
-NKERNEL = 16
+NKERNEL = 14
 
 _lib = None
 

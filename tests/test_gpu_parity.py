@@ -149,10 +149,18 @@ def test_resident_forward_general_fiber_weights():
     _assert_same(_run_resident(prob, 2, weights=w), _run_both(prob, 1, weights=w), prob.nshots, tol_g=1e-4)
 
 
-def test_tile_kernels_still_match_baseline():
-    """kernels = 2 (shared-memory tile kernels, the previous default) stays a valid cross-check path."""
-    prob = problems.small()
-    _assert_same(_run_both(prob, 2, batch=3), _run_both(prob, 1, batch=3), prob.nshots)
+@pytest.mark.parametrize("merge", ["0", "1"])
+def test_reverse_time_step_merged_and_separate_launches(merge, monkeypatch):
+    """The reverse-time step as one launch (reconstruction and adjoint CTAs side by side, the default) and as two launches
+    give the same gradient as the unfused baseline kernels -- and the same bits as each other (same per-item arithmetic)."""
+    monkeypatch.setenv("SEPFWI_MERGE_BWD", merge)
+    prob = problems.medium()
+    got = _run_both(prob, 3)
+    _assert_same(got, _run_both(prob, 1), prob.nshots)
+    monkeypatch.setenv("SEPFWI_MERGE_BWD", "1" if merge == "0" else "0")
+    other = _run_both(prob, 3)
+    for k in ("glam", "gmu", "grho"):
+        assert np.array_equal(got[1][k], other[1][k]), k
 
 
 def test_cpml_profiles_match_oracle():
