@@ -157,6 +157,10 @@ int sepfwi_plan_resident(const sepfwi_params *p, int nshots, int nsm, size_t sme
  * {first owned column, first row, end row, 1 if the warp takes the CPML path}; *n = number of entries (may exceed cap). */
 int sepfwi_plan_stream(const sepfwi_params *p, int nshots, int nsm, int which, int *items4, int cap, int *n);
 int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
+/* The misfit of the last sepfwi_gradient call in double precision (the float* argument mirrors the reference's float). */
+int sepfwi_last_misfit(sepfwi_handle *h, double *misfit);
+/* Host-only: device bytes per unit of max_batch that sepfwi_create would allocate for these parameters (max_batch ignored). */
+long long sepfwi_bytes_per_slot(const sepfwi_params *p);
 
 /* Per-kernel device timing: with nsteps > 0 every launch of the first nsteps time steps of each
  * time loop is bracketed by a CUDA-event pair on the launching stream; sepfwi_get_profile returns

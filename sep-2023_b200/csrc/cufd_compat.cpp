@@ -103,12 +103,33 @@ bool read_first_line(const std::string &fname, std::string &line)
     return true;
 }
 
+// One cached handle per (GPU, grid, mode).  `use` serialises the calls that share a handle (a handle is single-threaded,
+// include/sepfwi.h); the shared_ptr keeps it alive for a call that is still running when another call replaces the entry.
 struct Cached {
     sepfwi_handle *h = nullptr;
+    int maxrec = 0;
+    std::mutex use;
     ~Cached() { if (h) sepfwi_destroy(h); }
 };
 std::mutex g_mu;
-std::map<std::string, std::unique_ptr<Cached>> g_cache;
+std::map<std::string, std::shared_ptr<Cached>> g_cache;
+
+bool read_floats(const std::string &fn, float *dst, size_t n)
+{
+    FILE *fp = fopen(fn.c_str(), "rb");
+    if (!fp) return false;
+    const size_t got = fread(dst, sizeof(float), n, fp);
+    const bool more = got == n && fgetc(fp) != EOF;      // longer than expected: another nrec / nSteps wrote it
+    fclose(fp);
+    return got == n && !more;
+}
+bool write_floats(const std::string &fn, const float *src, size_t n)
+{
+    FILE *fp = fopen(fn.c_str(), "wb");
+    if (!fp) return false;
+    const size_t put = fwrite(src, sizeof(float), n, fp);
+    return fclose(fp) == 0 && put == n;
+}
 
 int efail(int code, const std::string &msg);
 
@@ -184,43 +205,58 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
         maxrec = nrec > maxrec ? nrec : maxrec;
     }
 
+    std::string scratch;
+    if (const JVal *sc = para.get("scratch_dir_name")) if (sc->kind == JVal::Str) scratch = sc->str;
+
     // handle cache
     char keybuf[512];
     snprintf(keybuf, sizeof(keybuf), "%d|%d|%d|%d|%d|%d|%.9g|%.9g|%.9g|%.9g|%d|%d|%d|%d", gpu_id, (int)nz, (int)nx, npml, (int)nPad, nS,
              dz, dx, dt, f0, fiber, calc_id == 1, (int)max_batch, race_compat);
-    std::unique_lock<std::mutex> lk(g_mu);
-    std::unique_ptr<Cached> &slot = g_cache[keybuf];
-    sepfwi_handle *h = slot ? slot->h : nullptr;
-    // a cached handle must be able to hold this call's receiver count
-    static std::map<std::string, int> cap;
-    if (h && cap[keybuf] < maxrec) { slot.reset(); h = nullptr; }
-    if (!h) {
+    std::shared_ptr<Cached> ent;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        std::shared_ptr<Cached> &slot = g_cache[keybuf];
+        // a cached handle must be able to hold this call's receiver count; a call still using the old one keeps it alive
+        if (slot && slot->maxrec < maxrec) slot.reset();
+        if (!slot) { slot = std::make_shared<Cached>(); slot->maxrec = maxrec; }
+        ent = slot;
+    }
+    std::lock_guard<std::mutex> use(ent->use);       // held for the whole call: one thread per handle
+    if (!ent->h) {
         sepfwi_params p;
         memset(&p, 0, sizeof(p));
         p.nz = (int)nz; p.nx = (int)nx; p.nPml = npml; p.nPad = (int)nPad; p.nSteps = nS;
         p.dz = (float)dz; p.dx = (float)dx; p.dt = (float)dt; p.f0 = (float)f0;
-        p.fiber = fiber; p.flavour = SEPFWI_FLAVOUR_CPML; p.max_nrec = maxrec; p.with_adjoint = calc_id == 1; p.ref_race_compat = race_compat;
+        p.fiber = fiber; p.flavour = SEPFWI_FLAVOUR_CPML; p.max_nrec = ent->maxrec; p.with_adjoint = calc_id == 1; p.ref_race_compat = race_compat;
         int B = (int)max_batch;
-        if (B <= 0) {   // enough concurrent shots to give every launch a few million cells, within memory
+        const bool autoB = B <= 0;
+        if (autoB) {   // enough concurrent shots to give every launch a few million cells, within memory
             const double cells = (double)(p.nz - p.nPad) * p.nx;
             B = (int)(4.0e6 / cells) + 1;
             if (B > 16) B = 16;
             size_t fr = 0, tot = 0;
             if (cudaSetDevice(gpu_id) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess) {
-                const double per = (calc_id == 1 ? 5.0 * sepfwi_ring_len(&p) * nS * 4.0 + 29.0 * cells * 4.0 : 13.0 * cells * 4.0) +
-                                   4.0 * maxrec * nS * 4.0;
+                const double per = (double)sepfwi_bytes_per_slot(&p);
                 while (B > 1 && per * B > 0.6 * (double)fr) B--;
             }
         }
         if (B > group_size && group_size > 0) B = group_size;
-        p.max_batch = B;
-        int rc = sepfwi_create(&p, gpu_id, &h);
-        if (rc) { g_cache.erase(keybuf); return rc; }
-        slot.reset(new Cached());
-        slot->h = h;
-        cap[keybuf] = maxrec;
+        int rc;
+        for (;;) {
+            p.max_batch = B;
+            rc = sepfwi_create(&p, gpu_id, &ent->h);
+            if (rc != SEPFWI_ENOMEM || !autoB || B <= 1) break;
+            B = B / 2 > 1 ? B / 2 : 1;            // another tenant took the memory between the estimate and the allocation
+        }
+        if (rc) {
+            ent->h = nullptr;
+            std::lock_guard<std::mutex> lk(g_mu);
+            auto it = g_cache.find(keybuf);
+            if (it != g_cache.end() && it->second == ent) g_cache.erase(it);
+            return rc;
+        }
     }
-    lk.unlock();
+    sepfwi_handle *h = ent->h;
 
     int rc = sepfwi_set_model(h, Lambda, Mu, Den, SEPFWI_MEM_HOST, nullptr);
     if (rc) return rc;
@@ -234,21 +270,17 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
         if (rc) return rc;
         for (int i = 0; i < group_size; i++)
             for (int c = 0; c < 4; c++) {
-                FILE *fp = fopen(fname(comps[c], shot_ids[i]).c_str(), "wb");
-                if (!fp) return efail(SEPFWI_EIO, "File writing error! " + fname(comps[c], shot_ids[i]));
-                fwrite(sd[i].out[c].data(), sizeof(float), sd[i].out[c].size(), fp);
-                fclose(fp);
+                if (!write_floats(fname(comps[c], shot_ids[i]), sd[i].out[c].data(), sd[i].out[c].size()))
+                    return efail(SEPFWI_EIO, "File writing error! " + fname(comps[c], shot_ids[i]));
             }
         return 0;
     }
     for (int i = 0; i < group_size; i++) {
         sd[i].obs.assign((size_t)shots[i].nrec * nS, 0.f);
         const std::string fn = fname("ett", shot_ids[i]);
-        FILE *fp = fopen(fn.c_str(), "rb");
-        if (!fp) return efail(SEPFWI_EIO, "File reading error! Attempted to read " + fn);
-        size_t got = fread(sd[i].obs.data(), sizeof(float), sd[i].obs.size(), fp);
-        (void)got;
-        fclose(fp);
+        if (!read_floats(fn, sd[i].obs.data(), sd[i].obs.size()))
+            return efail(SEPFWI_EIO, "File reading error! " + fn + " is missing or does not hold nrec x nSteps = " +
+                                         std::to_string(shots[i].nrec) + " x " + std::to_string(nS) + " floats");
         shots[i].obs_ett = sd[i].obs.data();
         if (calc_id == 1 && grad_stf) shots[i].gstf = grad_stf + (size_t)i * nS;   // LOCAL shot index, libCUFD.cu:671-673
     }
@@ -256,6 +288,32 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
     rc = sepfwi_gradient(h, group_size, shots.data(), calc_id == 1, &J, grad_Lambda, grad_Mu, grad_Den, SEPFWI_MEM_HOST, nullptr);
     if (rc) return rc;
     if (misfit) *misfit = J;
+    if (!scratch.empty()) {
+        // debug side channel of libCUFD.cu:731-751: pressure residual (obs - syn, sample 0 zeroed as gpuMinus does,
+        // utilities.cu:154-167), synthetic pressure and the observed pressure as loaded.  The gradient pass records only the DAS
+        // component, so the pressure traces come from one more forward pass -- paid only when the option is set.
+        for (int i = 0; i < group_size; i++) {
+            for (int c = 0; c < 7; c++) shots[i].out[c] = nullptr;
+            sd[i].out[0].assign((size_t)shots[i].nrec * nS, 0.f);
+            shots[i].out[0] = sd[i].out[0].data();
+        }
+        rc = sepfwi_forward(h, group_size, shots.data(), SEPFWI_MEM_HOST, nullptr);
+        if (rc) return rc;
+        for (int i = 0; i < group_size; i++) {
+            const size_t n = (size_t)shots[i].nrec * nS;
+            std::vector<float> obs(n), res(n);
+            if (!read_floats(fname("pr", shot_ids[i]), obs.data(), n))
+                return efail(SEPFWI_EIO, "File reading error! " + fname("pr", shot_ids[i]));
+            for (int r = 0; r < shots[i].nrec; r++)
+                for (int t = 0; t < nS; t++)
+                    res[(size_t)r * nS + t] = t == 0 ? 0.f : obs[(size_t)r * nS + t] - sd[i].out[0][(size_t)r * nS + t];
+            const std::string id = std::to_string(shot_ids[i]);
+            if (!write_floats(scratch + "/Residual_Shot" + id + ".bin", res.data(), n) ||
+                !write_floats(scratch + "/Syn_Shot" + id + ".bin", sd[i].out[0].data(), n) ||
+                !write_floats(scratch + "/CondObs_Shot" + id + ".bin", obs.data(), n))
+                return efail(SEPFWI_EIO, "File writing error! " + scratch + "/*_Shot" + id + ".bin");
+        }
+    }
     return 0;
 }
 

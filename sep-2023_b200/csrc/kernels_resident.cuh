@@ -53,6 +53,8 @@ struct ResArgs {
 __host__ __device__ constexpr size_t rs_smem_bytes(int RPT)
 { return sizeof(float) * ((size_t)5 * RS_NG * RPT * RS_EW + 4 * RS_PW * RS_EW + (size_t)4 * RS_NG * RPT * RS_PW + 6 * RS_NG * RPT); }
 
+__device__ __forceinline__ int rs_ld_acquire(const int *p)
+{ int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ int rs_ld_relaxed(const int *p)
 { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void rs_st_relaxed(int *p, int v)
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(RS_NT, 1) k_resident_fwd(const KArgs a, const 
         // producer: stores above -> barrier -> fence + release by one thread.  consumer: relaxed polls of the step counter
         // (no L1 invalidation), then L2 loads (ld.cg) issued after the poll's branch.
         if (tid < 32 && !(ra.dbg & 8)) {
-            __threadfence();
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");      // release pattern: fence + relaxed store (MEMBAR.ALL.GPU; __threadfence() would be the sequentially consistent MEMBAR.SC.GPU)
             if (outbox) rs_st_relaxed(outbox, it + 1);
         }
         if (!(ra.dbg & 1)) {
@@ -336,6 +338,14 @@ __global__ void __launch_bounds__(RS_NT, 1) k_resident_fwd(const KArgs a, const 
                 if (__all_sync(0xffffffffu, v >= it + 1)) break;
                 if (++spins > RS_SPIN_MAX || ((spins & 255) == 0 && *(volatile int *)ra.err)) { *ra.err = 1; dead = 1; break; }
             }
+            // acquire side of the exchange: the polls above are relaxed loads, and a control dependency does not order the halo
+            // loads after them in the PTX memory model.  Once every flag has arrived, the polling lanes re-read theirs with ONE
+            // ld.acquire (pairs with the producer's fence + relaxed store) and bar.warp.sync extends the order to the lanes
+            // that did not poll.  -DRS_RELAXED_EXCHANGE drops it (what round 1 shipped: works on sm_100a, not guaranteed).
+#ifndef RS_RELAXED_EXCHANGE
+            if (lane < 9 && lane != 4) (void)rs_ld_acquire(inbox + lane);
+            __syncwarp();
+#endif
             const float *vin = st + (size_t)(((it + 1) & 1) ? S_FWD1 : S_FWD) * fsz;
 #pragma unroll
             for (int k = 0; k < HPT; k++) {

@@ -489,6 +489,31 @@ extern "C" int sepfwi_get_cpml(sepfwi_handle *h, int axis, float *out)
 extern "C" long long sepfwi_launch_count(sepfwi_handle *h) { return h ? h->launches : 0; }
 extern "C" long long sepfwi_resident_launches(sepfwi_handle *h) { return h ? h->res_used : 0; }
 
+extern "C" int sepfwi_last_misfit(sepfwi_handle *h, double *misfit)
+{
+    if (!h || !misfit) return fail(SEPFWI_EINVAL, "null argument");
+    *misfit = h->last_misfit;
+    return 0;
+}
+
+// Device bytes one concurrent shot ("slot") costs on a handle created with these parameters -- what sepfwi_create allocates
+// per unit of max_batch (state block, boundary ring, traces, gradients, slot tables); host arithmetic only.
+extern "C" long long sepfwi_bytes_per_slot(const sepfwi_params *pp)
+{
+    if (!pp) return fail(SEPFWI_EINVAL, "null params");
+    Dims d;
+    int rc = fill_dims(*pp, d);
+    if (rc) return rc;
+    const bool sponge = pp->flavour == SEPFWI_FLAVOUR_SPONGE;
+    const size_t nTrace = sponge ? NTRACE : 4;
+    size_t b = (size_t)(pp->with_adjoint ? NSTATE : NSTATE_FWD) * d.fsz * sizeof(float);
+    b += nTrace * (size_t)d.maxRec * d.nSteps * sizeof(float) + (size_t)d.nSteps * sizeof(float);
+    if (pp->with_adjoint) b += (size_t)NFIELD * d.nSteps * d.ringLen * sizeof(float) + 3 * d.fsz * sizeof(float);
+    const size_t nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
+    b += (size_t)(50 * d.maxRec + 8 + nStrips * (d.nzA + 1)) * sizeof(int) + (size_t)(d.nSteps + 11 * d.maxRec) * sizeof(float);
+    return (long long)b;
+}
+
 extern "C" int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms)
 {
     if (!h) return fail(SEPFWI_EINVAL, "null handle");

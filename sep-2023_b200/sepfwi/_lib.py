@@ -37,7 +37,8 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_courant", "sepfwi_forward", "sepfwi_gradient", "sepfwi_cufd", "sepfwi_cufd_clear_cache",
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
-           "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots", "sepfwi_plan_resident", "sepfwi_plan_stream"]
+           "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots", "sepfwi_plan_resident", "sepfwi_plan_stream",
+           "sepfwi_last_misfit", "sepfwi_bytes_per_slot"]
 NKERNEL = 14
 
 _lib = None
@@ -79,6 +80,9 @@ def lib():
         L.sepfwi_resident_launches.argtypes = [C.c_void_p]
         L.sepfwi_resident_launches.restype = C.c_longlong
         L.sepfwi_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.sepfwi_last_misfit.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.sepfwi_bytes_per_slot.argtypes = [C.POINTER(Params)]
+        L.sepfwi_bytes_per_slot.restype = C.c_longlong
         L.sepfwi_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.sepfwi_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         L.sepfwi_kernel_name.argtypes = [C.c_int]

@@ -142,6 +142,10 @@ class Propagator(object):
         """Cooperative launches of the shared-memory-resident forward loop so far (0: the streaming kernels ran)."""
         return int(lib().sepfwi_resident_launches(self._h))
 
+    def bytes_per_slot(self):
+        """Device bytes per unit of max_batch for this handle's parameters."""
+        return int(lib().sepfwi_bytes_per_slot(C.byref(self.params)))
+
     def last_timing(self):
         f, b = C.c_float(), C.c_float()
         check(lib().sepfwi_last_timing(self._h, C.byref(f), C.byref(b)))
@@ -231,10 +235,12 @@ class Propagator(object):
         check(lib().sepfwi_forward_snapshots(self._h, arr, int(save_step), snaps.ctypes.data, _lib.MEM_HOST, self._stream()))
         return d, snaps
 
-    def gradient(self, shots, obs, with_adj=True, device=False, want_syn=False):
+    def gradient(self, shots, obs, with_adj=True, device=False, want_syn=False, grad_out=None):
         """Misfit and gradient of `shots` against observed DAS data `obs` (list of [nrec, nSteps]).
         device=True: obs are CUDA tensors and the gradients are returned as CUDA tensors.
-        Returns dict(misfit, glam, gmu, grho, gstf[list], syn[list])."""
+        grad_out: optional (glam, gmu, grho) float32 (nz, nx) contiguous CUDA tensors (device=True) the library writes
+        into -- e.g. views of a persistent packed all-reduce buffer (sepfwi.dist.PackedGradients).
+        Returns dict(misfit, misfit64, glam, gmu, grho, gstf[list], syn[list])."""
         keep = []
         arr = self._shot_array(shots, keep)
         gstf, syn = [], []
@@ -263,7 +269,14 @@ class Propagator(object):
         ptrs = [None, None, None]
         if with_adj:
             for k in range(3):
-                if device:
+                if device and grad_out is not None:
+                    g = grad_out[k]
+                    if (not g.is_cuda or g.device.index != self.device or not g.is_contiguous()
+                            or tuple(g.shape) != (self.nz, self.nx) or str(g.dtype) != "torch.float32"):
+                        raise ValueError("grad_out[%d] must be a contiguous float32 (nz, nx) tensor on cuda:%d" % (k, self.device))
+                    g3[k] = g
+                    ptrs[k] = g.data_ptr()
+                elif device:
                     import torch
                     g3[k] = torch.empty((self.nz, self.nx), dtype=torch.float32, device="cuda:%d" % self.device)
                     ptrs[k] = g3[k].data_ptr()
@@ -273,4 +286,6 @@ class Propagator(object):
         check(lib().sepfwi_gradient(self._h, len(shots), arr, 1 if with_adj else 0, C.byref(misfit),
                                     ptrs[0], ptrs[1], ptrs[2], _lib.MEM_DEVICE if device else _lib.MEM_HOST,
                                     self._stream()))
-        return dict(misfit=misfit.value, glam=g3[0], gmu=g3[1], grho=g3[2], gstf=gstf, syn=syn)
+        m64 = C.c_double(0.0)
+        check(lib().sepfwi_last_misfit(self._h, C.byref(m64)))
+        return dict(misfit=misfit.value, misfit64=m64.value, glam=g3[0], gmu=g3[1], grho=g3[2], gstf=gstf, syn=syn)

@@ -35,6 +35,7 @@ def clear_cache():
             p.close()
         _PROPS.clear()
         _OBS.clear()
+    dist.clear_packed()
 
 
 def _torch():
@@ -42,13 +43,17 @@ def _torch():
     return torch
 
 
-def auto_batch(nz, nx, nPad, nSteps, nrec, nPml, with_adjoint, nshots, device):
-    """Concurrent shots per launch: enough to give every launch a few million cells, within memory."""
+def auto_batch(nz, nx, nPad, nSteps, nrec, nPml, with_adjoint, nshots, device, params=None):
+    """Concurrent shots per launch: enough to give every launch a few million cells, within memory.  The bytes one slot
+    costs come from the library (sepfwi_bytes_per_slot: state block, boundary ring, traces, gradients, tables) plus the
+    device-cached observed data of the shot; at most 60 % of what is free now."""
     torch = _torch()
     cells = float((nz - nPad) * nx)
     B = min(32, int(4.0e6 / cells) + 1)      # small grids: one launch for the whole survey beats two (whole waves of latency-bound warps)
-    ring = 10.0 * ((nz - nPad - 2 * nPml + 4) + (nx - 2 * nPml + 4))
-    per = (5.0 * ring * nSteps * 4 + 29.0 * cells * 4 if with_adjoint else 13.0 * cells * 4) + 4.0 * nrec * nSteps * 4
+    if params is None:
+        params = _lib.Params(int(nz), int(nx), int(nPml), int(nPad), int(nSteps), 1.0, 1.0, 1.0, 1.0, 0, 0, 1, max(1, int(nrec)),
+                             1 if with_adjoint else 0, 0, 0)
+    per = float(_lib.lib().sepfwi_bytes_per_slot(params)) + 4.0 * nrec * nSteps
     free = torch.cuda.mem_get_info(device)[0]
     while B > 1 and per * B > 0.6 * free:
         B -= 1
@@ -67,11 +72,16 @@ def _prop(para, device, with_adjoint, nrec, nshots):
         if p is not None and (p.params.max_nrec < nrec or p.params.max_batch < min(B, nshots)):
             p.close()
             p = None
-        if p is None:
-            p = Propagator(para["nz"], para["nx"], para["nPoints_pml"], para["nPad"], para["nSteps"], para["dz"],
-                           para["dx"], para["dt"], para["f0"], fiber=fiber, max_batch=B, max_nrec=nrec,
-                           with_adjoint=with_adjoint, device=device, ref_race_compat=race)
-            _PROPS[key] = p
+        while p is None:
+            try:
+                p = Propagator(para["nz"], para["nx"], para["nPoints_pml"], para["nPad"], para["nSteps"], para["dz"],
+                               para["dx"], para["dt"], para["f0"], fiber=fiber, max_batch=B, max_nrec=nrec,
+                               with_adjoint=with_adjoint, device=device, ref_race_compat=race)
+            except _lib.SepfwiError as e:
+                if e.code != -5 or B <= 1:       # SEPFWI_ENOMEM: other tenants of the GPU; halve the batch and retry
+                    raise
+                B = max(1, B // 2)
+        _PROPS[key] = p
     return p
 
 
@@ -84,22 +94,36 @@ def _shots(para, shot_ids, Stf):
             for s, sid in zip(sv, shot_ids)], stf.shape
 
 
+_OBS_CAP_BYTES = 64 << 30      # device bytes the observed-data cache may hold per process (least recently used goes first)
+
+
 def _obs(para, sid, nrec, device):
-    """Shot_ett{id}.bin (libCUFD.cu:221-223), cached on the device keyed by path + mtime + size."""
+    """Shot_ett{id}.bin (libCUFD.cu:221-223), cached on the device.  One entry per (path, device): a regenerated file
+    (other mtime / size) REPLACES its entry, and the cache as a whole is bounded (LRU)."""
     torch = _torch()
     path = os.path.join(para["data_dir_name"], "Shot_ett%d.bin" % int(sid))
     try:
         st = os.stat(path)
     except OSError:
         raise RuntimeError("File reading error! Attempted to read %s" % path)
-    key = (path, st.st_mtime_ns, st.st_size, device)
-    t = _OBS.get(key)
-    if t is None:
-        a = np.fromfile(path, np.float32)
-        if a.size != nrec * para["nSteps"]:
-            raise RuntimeError("%s holds %d floats, expected %d x %d" % (path, a.size, nrec, para["nSteps"]))
-        t = torch.from_numpy(a.reshape(nrec, para["nSteps"])).to("cuda:%d" % device)
-        _OBS[key] = t
+    key, stamp = (path, device), (st.st_mtime_ns, st.st_size)
+    with _LOCK:
+        ent = _OBS.pop(key, None)
+        if ent is not None and ent[0] == stamp:
+            _OBS[key] = ent                       # re-inserted last: most recently used
+            return ent[1]
+    a = np.fromfile(path, np.float32)
+    if a.size != nrec * para["nSteps"]:
+        raise RuntimeError("%s holds %d floats, expected %d x %d" % (path, a.size, nrec, para["nSteps"]))
+    t = torch.from_numpy(a.reshape(nrec, para["nSteps"])).to("cuda:%d" % device)
+    with _LOCK:
+        _OBS[key] = (stamp, t)
+        total = sum(v[1].numel() * 4 for v in _OBS.values())
+        for k in list(_OBS):
+            if total <= _OBS_CAP_BYTES or k == key:
+                break
+            total -= _OBS[k][1].numel() * 4
+            del _OBS[k]
     return t
 
 
@@ -131,8 +155,10 @@ def _model_on(device, *tensors):
     return out
 
 
-def _gradient_on_device(device, Lambda, Mu, Den, Stf, ids, para, with_adj):
-    """Misfit (+gradients) of shots `ids` on one GPU.  Returns (misfit, gl, gm, gd, gstf_full) with CUDA tensors."""
+def _gradient_on_device(device, Lambda, Mu, Den, Stf, ids, para, with_adj, packed=False):
+    """Misfit (+gradients) of shots `ids` on one GPU.  Returns (misfit, gl, gm, gd, gstf_full) with CUDA tensors; with
+    packed=True the gradients are written straight into this device's persistent all-reduce buffer and the
+    dist.PackedGradients object is returned instead."""
     torch = _torch()
     with torch.cuda.device(device):
         shots, stf_shape = _shots(para, ids, Stf)
@@ -141,12 +167,19 @@ def _gradient_on_device(device, Lambda, Mu, Den, Stf, ids, para, with_adj):
         lam, mu, den = _model_on(device, Lambda, Mu, Den)
         P.set_model(lam, mu, den)
         obs = [_obs(para, sid, s.nrec, device) for sid, s in zip(ids, shots)]
+        if packed:
+            pk = dist.packed_for((para["nz"], para["nx"]), stf_shape, "cuda:%d" % device)
+            r = P.gradient(shots, obs, with_adj=True, device=True, grad_out=pk.views())
+            pk.set_local(r["misfit64"], dict(zip(ids, r["gstf"])))
+            return pk
         r = P.gradient(shots, obs, with_adj=with_adj, device=True)
         gstf = torch.zeros(stf_shape, dtype=torch.float32, device="cuda:%d" % device)
         if with_adj:
+            stage = torch.zeros(stf_shape, dtype=torch.float32)
             for sid, g in zip(ids, r["gstf"]):
-                gstf[sid] = torch.from_numpy(g).to(gstf.device)
-        return r["misfit"], r["glam"], r["gmu"], r["grho"], gstf
+                stage[int(sid)] = torch.from_numpy(g)
+            gstf.copy_(stage)
+        return r["misfit64"], r["glam"], r["gmu"], r["grho"], gstf
 
 
 def forward(Lambda, Mu, Den, Stf, gpu_id, Shot_ids, para_fname):
@@ -165,8 +198,9 @@ def backward(Lambda, Mu, Den, Stf, ngpu, Shot_ids, para_fname):
     if dist.is_distributed():
         ws, rank = dist.world()
         dev = _dev_of(Lambda)
-        J, gl, gm, gd, gs = _gradient_on_device(dev, Lambda, Mu, Den, Stf, dist.shard(ids, ws, rank), para, True)
-        J, gl, gm, gd, gs = dist.allreduce_gradients(J, gl, gm, gd, gs)
+        pk = _gradient_on_device(dev, Lambda, Mu, Den, Stf, dist.shard(ids, ws, rank), para, True, packed=True)
+        J, gl, gm, gd, gs = pk.allreduce()
+        gl, gm, gd, gs = gl.clone(), gm.clone(), gd.clone(), gs.clone()      # the packed buffer is reused by the next call
     elif int(ngpu) <= 1:
         J, gl, gm, gd, gs = _gradient_on_device(_dev_of(Lambda), Lambda, Mu, Den, Stf, ids, para, True)
     else:
