@@ -399,8 +399,15 @@ def main():
 
 
 def git_head():
+    """Commit of the tree being measured: git where there is one, else what build() recorded next to the library."""
     try:
-        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=10).stdout.strip() or None
+        h = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=10).stdout.strip()
+        if h:
+            return h
+    except Exception:
+        pass
+    try:
+        return json.load(open(os.path.join(ROOT, "sep-2023_b200", "build_info.json"))).get("commit")
     except Exception:
         return None
 

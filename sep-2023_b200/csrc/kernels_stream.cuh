@@ -37,12 +37,33 @@ struct StreamArgs {
     int q, pa;                       // backward: forward buffer holding state it+1, adjoint buffer holding adj(it+1)
     const int4 *work;                // work list, one entry per warp: {x0 = first owned column, z0, z1 = owned rows [z0, z1), 1 if edge}
     int nWork;                       //   edge entries (CPML strips / inactive rim) come first: they are the slow ones
+    int nEdge;                       //   number of edge entries
     int nAux;                        // leading CTAs doing the perimeter work
     int nrecMax;                     // largest receiver count over the slots of this batch
     int force;                       // debug/timing only: 1 = every warp takes the interior path (wrong at the edges), 2 = every warp the edge path
 };
 
 #define Q4(v) {v.x, v.y, v.z, v.w}
+// Register windows are LINEAR: slot j of a 6-slot window holds row (first row of the trip) - 2 + j for the fields that are read
+// ahead (rows r-2 .. r+2 of the iteration at row r sit in slots u .. u+4) and row (first row of the trip) - 4 + j for the fields
+// the iteration produces (rows r-4 .. r in slots u .. u+4), u = the row's position inside the loop trip.  A trip of UNR rows ends
+// by moving every window down UNR slots.  UNR = 6 needs no moves (the indices wrap), but its loop body (6 x ~0.6-1.5 k
+// instructions) overflows the 32 KB L1.5 instruction cache: ncu showed 0.6 - 2.0 no_instruction stalls per issued instruction.
+template <int S> __device__ __forceinline__ void win_shift(float4 (&a)[6])
+{
+#pragma unroll
+    for (int j = 0; j + S < 6; j++) a[j] = a[j + S];
+}
+// (6-slot windows: 1, 2 or 6 rows per trip)
+#ifndef SW_UNR_FWD
+#define SW_UNR_FWD 2
+#endif
+#ifndef SW_UNR_ADJ
+#define SW_UNR_ADJ 2
+#endif
+#ifndef SW_UNR_REC
+#define SW_UNR_REC 2
+#endif
 // Programmatic dependent launch: every kernel of a time loop lets its successor start launching right away and
 // waits for its predecessor's results only after its own set-up -- removes the ~2-4 us launch gap per time step.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -270,7 +291,7 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
                 if (k.xq0 + c == k.xs) { nzz[c] += amp; nxx[c] += amp; }
         }
         const float4 rzz = mk4(nzz), rxz = mk4(nxz), rxx = mk4(nxx);
-        w.zz[u % 6] = rzz; w.xz[u % 6] = rxz; w.xx[u % 6] = rxx;          // stress row r lives in slot u
+        w.zz[(u + 4) % 6] = rzz; w.xz[(u + 4) % 6] = rxz; w.xx[(u + 4) % 6] = rxx;          // new stress row r-j lives in slot u+4-j
         if (k.lown && rown) {
             stq(k.o + F_SZZ * fsz + ro, rzz); stq(k.o + F_SXZ * fsz + ro, rxz); stq(k.o + F_SXX * fsz + ro, rxx);
             if (EDGE) {
@@ -279,12 +300,12 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
             }
         }
     }
-    // ---- velocity at row q = r-2 : szz rows q-1..q+2, sxz rows q-2..q+1, sxx row q (stress row r-j lives in slot u-j)
+    // ---- velocity at row q = r-2 : szz rows q-1..q+2, sxz rows q-2..q+1, sxx row q (stress row r-j lives in slot u+4-j)
     {
         const int q = r - 2;
-        const float4 p0 = w.zz[(u + 3) % 6], p1 = w.zz[(u + 4) % 6], p2 = w.zz[(u + 5) % 6], p3 = w.zz[u % 6];
-        const float4 q0 = w.xz[(u + 2) % 6], q1 = w.xz[(u + 3) % 6], q2 = w.xz[(u + 4) % 6], q3 = w.xz[(u + 5) % 6];
-        const float4 xc = w.xx[(u + 4) % 6];
+        const float4 p0 = w.zz[(u + 1) % 6], p1 = w.zz[(u + 2) % 6], p2 = w.zz[(u + 3) % 6], p3 = w.zz[(u + 4) % 6];
+        const float4 q0 = w.xz[u % 6], q1 = w.xz[(u + 1) % 6], q2 = w.xz[(u + 2) % 6], q3 = w.xz[(u + 3) % 6];
+        const float4 xc = w.xx[(u + 2) % 6];
         const float xzc[7] = XWIN_B(q2), xxc[7] = XWIN_F(xc);
         const float zzm1[4] = Q4(p0), zzc[4] = Q4(p1), zzp1[4] = Q4(p2), zzp2[4] = Q4(p3);
         const float xzm2[4] = Q4(q0), xzm1[4] = Q4(q1), xzp1[4] = Q4(q3);
@@ -411,27 +432,23 @@ __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs
 #pragma unroll
     for (int j = 0; j < NST - 1; j++) stream_fwd_issue<EDGE>(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
-    if (!EDGE) {
-        // interior: rotate the windows by full unrolling (6 rows per trip); surplus rows of the last trip are computed and dropped
+    // UNR rows per trip, then the windows move down UNR slots; surplus rows of the last trip are computed and dropped.
+    // Edge warps: one row per trip (their body is much longer).
+    constexpr int UNR = EDGE ? 1 : SW_UNR_FWD;
+    static_assert(UNR == 1 || UNR == 2 || UNR == 6, "6-slot windows: 1, 2 or 6 rows per trip");
+    int stage = 0;
 #pragma unroll 1
-        for (int kk = 0; kk < niter; kk += 6) {
-            const int r = r0 + kk;
-            stream_fwd_row<EDGE, 0>(k, w, r, 0 % NST);     stream_fwd_row<EDGE, 1>(k, w, r + 1, 1 % NST); stream_fwd_row<EDGE, 2>(k, w, r + 2, 2 % NST);
-            stream_fwd_row<EDGE, 3>(k, w, r + 3, 3 % NST); stream_fwd_row<EDGE, 4>(k, w, r + 4, 4 % NST); stream_fwd_row<EDGE, 5>(k, w, r + 5, 5 % NST);
+    for (int kk = 0; kk < niter; kk += UNR) {
+        const int r = r0 + kk;
+        stream_fwd_row<EDGE, 0>(k, w, r, stage); stage = stage == NST - 1 ? 0 : stage + 1;
+        if (UNR > 1) { stream_fwd_row<EDGE, 1 % UNR>(k, w, r + 1, stage); stage = stage == NST - 1 ? 0 : stage + 1; }
+        if (UNR > 2) { stream_fwd_row<EDGE, 2 % UNR>(k, w, r + 2, stage); stage = stage == NST - 1 ? 0 : stage + 1; }
+        if (UNR > 3) {
+            stream_fwd_row<EDGE, 3 % UNR>(k, w, r + 3, stage); stage = stage == NST - 1 ? 0 : stage + 1;
+            stream_fwd_row<EDGE, 4 % UNR>(k, w, r + 4, stage); stage = stage == NST - 1 ? 0 : stage + 1;
+            stream_fwd_row<EDGE, 5 % UNR>(k, w, r + 5, stage); stage = stage == NST - 1 ? 0 : stage + 1;
         }
-    } else {
-        // edge: one row per trip and explicit register moves, so the (much longer) body stays resident in the instruction cache
-        int stage = 0;
-#pragma unroll 1
-        for (int kk = 0; kk < niter; kk++) {
-            stream_fwd_row<EDGE, 0>(k, w, r0 + kk, stage);
-            stage = stage == NST - 1 ? 0 : stage + 1;
-#pragma unroll
-            for (int j = 0; j < 4; j++) { w.vz[j] = w.vz[j + 1]; w.vx[j] = w.vx[j + 1]; }
-            w.zz[3] = w.zz[4]; w.zz[4] = w.zz[5]; w.zz[5] = w.zz[0];
-            w.xz[2] = w.xz[3]; w.xz[3] = w.xz[4]; w.xz[4] = w.xz[5]; w.xz[5] = w.xz[0];
-            w.xx[4] = w.xx[5]; w.xx[5] = w.xx[0];
-        }
+        if (UNR < 6) { win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); win_shift<UNR>(w.zz); win_shift<UNR>(w.xz); win_shift<UNR>(w.xx); }
     }
     cp_wait<0>();
 }
@@ -674,15 +691,15 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
         }
         if (k.anyinj) stream_adj_inject(k, r, nvz, nvx);
         const float4 rvz = mk4(nvz), rvx = mk4(nvx);
-        w.vz[u % 6] = rvz; w.vx[u % 6] = rvx;              // new adjoint velocity row r lives in slot u
+        w.vz[(u + 4) % 6] = rvz; w.vx[(u + 4) % 6] = rvx;              // new adjoint velocity row r-j lives in slot u+4-j
         if (k.lown && rown) { stq(k.o + F_VZ * fsz + ro, rvz); stq(k.o + F_VX * fsz + ro, rvx); }
     }
     if (EDGE) __syncwarp();      // phase B reads CPML memory written by other lanes of this warp
-    // ---- phase B: adjoint stresses at row q = r-2 from v^z rows q-2..q+1, v^x rows q-1..q+2 (row r-j lives in slot u-j)
+    // ---- phase B: adjoint stresses at row q = r-2 from v^z rows q-2..q+1, v^x rows q-1..q+2 (row r-j lives in slot u+4-j)
     {
         const int q = r - 2;
-        const float4 v0 = w.vz[(u + 2) % 6], v1 = w.vz[(u + 3) % 6], v2 = w.vz[(u + 4) % 6], v3 = w.vz[(u + 5) % 6];
-        const float4 u0 = w.vx[(u + 3) % 6], u1 = w.vx[(u + 4) % 6], u2 = w.vx[(u + 5) % 6], u3 = w.vx[u % 6];
+        const float4 v0 = w.vz[u % 6], v1 = w.vz[(u + 1) % 6], v2 = w.vz[(u + 2) % 6], v3 = w.vz[(u + 3) % 6];
+        const float4 u0 = w.vx[(u + 1) % 6], u1 = w.vx[(u + 2) % 6], u2 = w.vx[(u + 3) % 6], u3 = w.vx[(u + 4) % 6];
         const float wvz[7] = XWIN_F(v2), wvx[7] = XWIN_B(u1);
         const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
         const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
@@ -841,25 +858,21 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
 #pragma unroll
     for (int j = 0; j < (EDGE ? AR_NST_E : AR_NST) - 1; j++) stream_adj_issue<EDGE>(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
-    if (!EDGE) {
+    constexpr int UNR = EDGE ? 1 : SW_UNR_ADJ, NST = EDGE ? AR_NST_E : AR_NST;
+    int stg = 0;
 #pragma unroll 1
-        for (int kk = 0; kk < niter; kk += 6) {
-            const int r = r0 + kk;
-            stream_adj_row<EDGE, 0>(k, w, r, 0 % AR_NST);     stream_adj_row<EDGE, 1>(k, w, r + 1, 1 % AR_NST); stream_adj_row<EDGE, 2>(k, w, r + 2, 2 % AR_NST);
-            stream_adj_row<EDGE, 3>(k, w, r + 3, 3 % AR_NST); stream_adj_row<EDGE, 4>(k, w, r + 4, 4 % AR_NST); stream_adj_row<EDGE, 5>(k, w, r + 5, 5 % AR_NST);
+    for (int kk = 0; kk < niter; kk += UNR) {
+        const int r = r0 + kk;
+        stream_adj_row<EDGE, 0>(k, w, r, stg); stg = stg == NST - 1 ? 0 : stg + 1;
+        if (UNR > 1) { stream_adj_row<EDGE, 1 % UNR>(k, w, r + 1, stg); stg = stg == NST - 1 ? 0 : stg + 1; }
+        if (UNR > 2) { stream_adj_row<EDGE, 2 % UNR>(k, w, r + 2, stg); stg = stg == NST - 1 ? 0 : stg + 1; }
+        if (UNR > 3) {
+            stream_adj_row<EDGE, 3 % UNR>(k, w, r + 3, stg); stg = stg == NST - 1 ? 0 : stg + 1;
+            stream_adj_row<EDGE, 4 % UNR>(k, w, r + 4, stg); stg = stg == NST - 1 ? 0 : stg + 1;
+            stream_adj_row<EDGE, 5 % UNR>(k, w, r + 5, stg); stg = stg == NST - 1 ? 0 : stg + 1;
         }
-    } else {
-        int stg = 0;
-#pragma unroll 1
-        for (int kk = 0; kk < niter; kk++) {
-            stream_adj_row<EDGE, 0>(k, w, r0 + kk, stg);
-            stg = stg == AR_NST_E - 1 ? 0 : stg + 1;
-#pragma unroll
-            for (int j = 0; j < 4; j++) { w.sz[j] = w.sz[j + 1]; w.sx[j] = w.sx[j + 1]; w.sxz[j] = w.sxz[j + 1]; }
-            w.vz[2] = w.vz[3]; w.vz[3] = w.vz[4]; w.vz[4] = w.vz[5]; w.vz[5] = w.vz[0];
-            w.vx[3] = w.vx[4]; w.vx[4] = w.vx[5]; w.vx[5] = w.vx[0];
-            w.qxx[0] = w.qxx[1]; w.qxx[1] = w.qxx[2]; w.qxz[0] = w.qxz[1]; w.qxz[1] = w.qxz[2];
-        }
+        if (UNR < 6) { win_shift<UNR>(w.sz); win_shift<UNR>(w.sx); win_shift<UNR>(w.sxz); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); }
+        if (EDGE) { w.qxx[0] = w.qxx[1]; w.qxx[1] = w.qxx[2]; w.qxz[0] = w.qxz[1]; w.qxz[1] = w.qxz[2]; }
     }
     cp_wait<0>();
 }
@@ -993,7 +1006,7 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
             }
         }
         const float4 rvz = mk4(nvz), rvx = mk4(nvx);
-        w.vz[u % 6] = rvz; w.vx[u % 6] = rvx;
+        w.vz[(u + 4) % 6] = rvz; w.vx[(u + 4) % 6] = rvx;       // reconstructed velocity row r-j lives in slot u+4-j
         // grho gather (el_velocity.cu:104-110 sprays ga to (z,x),(z+1,x) and gb to (z,x),(z,x+1))
         const float gbl = sh_l(gb[3]);
         const bool rown = (r >= k.zc0) && (r < k.zc1);
@@ -1020,8 +1033,8 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
     // ---- stage 2: stresses of time `it` at row q = r-2 ; lambda / mu imaging
     {
         const int q = r - 2;
-        const float4 v0 = w.vz[(u + 2) % 6], v1 = w.vz[(u + 3) % 6], v2 = w.vz[(u + 4) % 6], v3 = w.vz[(u + 5) % 6];
-        const float4 u0 = w.vx[(u + 3) % 6], u1 = w.vx[(u + 4) % 6], u2 = w.vx[(u + 5) % 6], u3 = w.vx[u % 6];
+        const float4 v0 = w.vz[u % 6], v1 = w.vz[(u + 1) % 6], v2 = w.vz[(u + 2) % 6], v3 = w.vz[(u + 3) % 6];
+        const float4 u0 = w.vx[(u + 1) % 6], u1 = w.vx[(u + 2) % 6], u2 = w.vx[(u + 3) % 6], u3 = w.vx[(u + 4) % 6];
         const float wvz[7] = XWIN_F(v2), wvx[7] = XWIN_B(u1);
         const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
         const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
@@ -1131,27 +1144,20 @@ __device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs
 #pragma unroll
     for (int j = 0; j < RC_NST - 1; j++) stream_rec_issue(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
-    if (!EDGE) {
+    constexpr int UNR = EDGE ? 1 : SW_UNR_REC;
+    int stage = 0;
 #pragma unroll 1
-        for (int kk = 0; kk < niter; kk += 6) {
-            const int r = r0 + kk;
-            stream_rec_row<EDGE, 0>(k, w, r, 0 % RC_NST);     stream_rec_row<EDGE, 1>(k, w, r + 1, 1 % RC_NST); stream_rec_row<EDGE, 2>(k, w, r + 2, 2 % RC_NST);
-            stream_rec_row<EDGE, 3>(k, w, r + 3, 3 % RC_NST); stream_rec_row<EDGE, 4>(k, w, r + 4, 4 % RC_NST); stream_rec_row<EDGE, 5>(k, w, r + 5, 5 % RC_NST);
+    for (int kk = 0; kk < niter; kk += UNR) {
+        const int r = r0 + kk;
+        stream_rec_row<EDGE, 0>(k, w, r, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
+        if (UNR > 1) { stream_rec_row<EDGE, 1 % UNR>(k, w, r + 1, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1; }
+        if (UNR > 2) { stream_rec_row<EDGE, 2 % UNR>(k, w, r + 2, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1; }
+        if (UNR > 3) {
+            stream_rec_row<EDGE, 3 % UNR>(k, w, r + 3, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
+            stream_rec_row<EDGE, 4 % UNR>(k, w, r + 4, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
+            stream_rec_row<EDGE, 5 % UNR>(k, w, r + 5, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
         }
-    } else {
-        // edge: one row per trip and explicit register moves (keeps the long body inside the instruction cache)
-        int stage = 0;
-#pragma unroll 1
-        for (int kk = 0; kk < niter; kk++) {
-            stream_rec_row<EDGE, 0>(k, w, r0 + kk, stage);
-            stage = stage == RC_NST - 1 ? 0 : stage + 1;
-            // row r+j lives in slot 2+j (old stresses), row r-j in slot (6-j)%6 (new velocities): shift everything one row
-            w.szz[0] = w.szz[1]; w.szz[1] = w.szz[2]; w.szz[2] = w.szz[3]; w.szz[3] = w.szz[4];
-            w.sxz[0] = w.sxz[1]; w.sxz[1] = w.sxz[2]; w.sxz[2] = w.sxz[3];
-            w.sxx[0] = w.sxx[1]; w.sxx[1] = w.sxx[2];
-            w.vz[2] = w.vz[3]; w.vz[3] = w.vz[4]; w.vz[4] = w.vz[5]; w.vz[5] = w.vz[0];
-            w.vx[3] = w.vx[4]; w.vx[4] = w.vx[5]; w.vx[5] = w.vx[0];
-        }
+        if (UNR < 6) { win_shift<UNR>(w.szz); win_shift<UNR>(w.sxz); win_shift<UNR>(w.sxx); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); }
     }
     cp_wait<0>();
 }
@@ -1171,54 +1177,6 @@ __global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, 
     const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (RC_WARP_BYTES / 16);
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);
     else stream_rec_body<true>(a, sa, s, wk, lane, sw, sp);
-}
-
-// ================================================================================================
-// reverse-time step as ONE launch: reconstruction + imaging and the adjoint sweep are independent within a time step
-// (both read the adjoint state of buffer pa; one writes the forward buffer q^1 and the gradients, the other the adjoint
-// buffer pa^1), so their items share a launch.  CTA 2j+1 runs the reconstruction and CTA 2j+2 the adjoint sweep of the
-// SAME four (strip, chunk) items: the pair is dispatched together, and whichever of the two reads a row of the five
-// adjoint fields / five coefficient arrays second finds it in L2 -- on grids beyond the L2 that removes 40 of the
-// 164 bytes per cell the two separate launches move.  One launch per step also halves the launch / drain gaps on the
-// small grids.  grid: x = 1 + 2 ceil(nWork / SW_WPB), y = slot ; CTA 0 writes the stf gradient.
-constexpr size_t BW_ADJ_BYTES = AR_SMEM + (size_t)SW_WPB * 256 * sizeof(float);       // operand rings + the injection staging rows
-constexpr size_t BW_SMEM = RC_SMEM > BW_ADJ_BYTES ? RC_SMEM : BW_ADJ_BYTES;
-__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_bwd(const KArgs a, const StreamArgs sa)
-{
-    extern __shared__ __align__(16) float smem[];
-    pdl_launch_dependents();
-    const int s = blockIdx.y;
-    const Dims &d = a.d;
-    if (blockIdx.x == 0) {
-        pdl_wait();
-        if (threadIdx.x == 0) {      // source_grad, utilities.cu:719-730, from the adjoint state after step it+1
-            const float *src = slot_state(a, s) + (size_t)(sa.pa ? S_ADJ1 : S_ADJ) * d.fsz;
-            const size_t i = (size_t)a.t.zs[s] * d.ldx + a.t.xs[s];
-            a.gstf[(size_t)s * d.nSteps + sa.it] = -(src[(size_t)F_SZZ * d.fsz + i] + a.t.rxz[s] * src[(size_t)F_SXX * d.fsz + i]) * d.dt;
-        }
-        return;
-    }
-    const int b = (int)blockIdx.x - 1;
-    const int wi = (int)threadIdx.x >> 5;
-    const int wg = (b >> 1) * SW_WPB + wi;
-    if (wg >= sa.nWork) return;
-    const int4 wk = __ldg(sa.work + wg);
-    const int lane = threadIdx.x & 31;
-    const bool inner = (wk.w == 0 || sa.force == 1) && sa.force != 2;
-    if ((b & 1) == 0) {
-        const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + wi * RC_WARP_BYTES;
-        const float4 *sp = reinterpret_cast<const float4 *>(smem) + wi * (RC_WARP_BYTES / 16);
-        pdl_wait();
-        if (inner) stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);
-        else stream_rec_body<true>(a, sa, s, wk, lane, sw, sp);
-    } else {
-        const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + wi * AR_WARP_BYTES;
-        const float4 *sp = reinterpret_cast<const float4 *>(smem) + wi * (AR_WARP_BYTES / 16);
-        pdl_wait();
-        float *stage = smem + AR_SMEM / sizeof(float) + wi * 256;
-        if (inner) stream_adj_body<false>(a, sa, s, wk, lane, stage, sw, sp);
-        else stream_adj_body<true>(a, sa, s, wk, lane, stage, sw, sp);
-    }
 }
 
 }  // namespace sepfwi

@@ -63,7 +63,6 @@ struct sepfwi_handle {
     size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_sInjPtr, o_sInj;
     int nStrips = 0;
     bool stream = false;   // register-streaming kernels (kernels = 0 / 3); otherwise the unfused baseline kernels
-    bool merge_bwd = true; // reverse-time step as ONE launch: reconstruction and adjoint items of the same (strip, chunk) side by side
     int nSM = 148;
     size_t smem_optin = 0; // largest opt-in dynamic shared memory per block on this device
     bool pdl = true;       // programmatic dependent launch inside the time loops (SEPFWI_PDL=0 disables)
@@ -72,10 +71,11 @@ struct sepfwi_handle {
     // SEPFWI_LZ / SEPFWI_LZE chunk heights, SEPFWI_FORCE 1/2 force the interior / edge code path (timing only),
     // SEPFWI_PLAN_DEBUG prints the plans, SEPFWI_RES_DEBUG the resident kernel's timing switches
     int tune_lz = 0, tune_lze = 0, tune_force = 0, res_dbg = 0, res_forced_rpt = 0;
+    int smem_pad = 0;      // SEPFWI_SMEM_PAD: extra dynamic shared memory per streaming CTA (experiment: shrinks the L1 carve-out)
     bool plan_debug = false, res_fake_refuse = false;
     bool res_attr_done[16] = {false};      // cudaFuncSetAttribute issued for k_resident_fwd<RPT> on this handle's device
-    int4 *work[4] = {nullptr, nullptr, nullptr, nullptr};   // work lists of the streaming kernels (device): forward, reconstruction, adjoint, merged backward
-    size_t work_cap[4] = {0, 0, 0, 0};
+    int4 *work[3] = {nullptr, nullptr, nullptr};   // work lists of the streaming kernels (device): forward, reconstruction, adjoint
+    size_t work_cap[3] = {0, 0, 0};
     size_t o_amp, o_rxz, o_w, o_injCoef;
     bool use_w = false;
     // shared-memory-resident forward loop (kernels_resident.cuh): used when the tiles of a shot fit the SMs
@@ -98,9 +98,9 @@ struct sepfwi_handle {
     size_t hj_cap = 0, hg_cap = 0;
     double last_misfit = 0.0;                        // misfit of the last sepfwi_gradient call in double precision
     uint64_t staged_sig = 0;                         // signature of the batch the device slot tables hold (0: none)
-    uint64_t plan_sig[4] = {0, 0, 0, 0};             // ... and of the work lists (forward, reconstruction, adjoint, merged backward)
-    StreamArgs plan_sa[4];
-    int4 *work_host[4] = {nullptr, nullptr, nullptr, nullptr};    // pinned mirrors of the work lists
+    uint64_t plan_sig[3] = {0, 0, 0};                // ... and of the work lists (forward, reconstruction, adjoint)
+    StreamArgs plan_sa[3];
+    int4 *work_host[3] = {nullptr, nullptr, nullptr};    // pinned mirrors of the work lists
     cudaEvent_t ev[4];
     float fwd_ms = 0.f, bwd_ms = 0.f;
     static const int NBLK_RES = 64;
@@ -114,7 +114,7 @@ struct sepfwi_handle {
 };
 
 static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
-                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "stream_fwd", "stream_recon", "stream_adj", "stream_bwd", "resident_fwd"};
+                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "stream_fwd", "stream_recon", "stream_adj", "resident_fwd"};
 
 // Launch with programmatic stream serialization (the kernels call griddepcontrol.launch_dependents / .wait themselves).
 template <typename... KA, typename... A>
@@ -282,7 +282,7 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
                    h->dense[0], h->dense[1], h->dense[2], h->t_flt};
     for (float *q : fp) if (q) cudaFree(q);
     if (h->maxcp) cudaFree(h->maxcp);
-    for (int k = 0; k < 4; k++) { if (h->work[k]) cudaFree(h->work[k]); if (h->work_host[k]) cudaFreeHost(h->work_host[k]); }
+    for (int k = 0; k < 3; k++) { if (h->work[k]) cudaFree(h->work[k]); if (h->work_host[k]) cudaFreeHost(h->work_host[k]); }
     if (h->partial) cudaFree(h->partial);
     if (h->misfit) cudaFree(h->misfit);
     if (h->t_int) cudaFree(h->t_int);
@@ -368,11 +368,11 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     if (const char *e = getenv("SEPFWI_LZ")) h->tune_lz = atoi(e);
     if (const char *e = getenv("SEPFWI_LZE")) h->tune_lze = atoi(e);
     if (const char *e = getenv("SEPFWI_FORCE")) h->tune_force = atoi(e);
+    if (const char *e = getenv("SEPFWI_SMEM_PAD")) h->smem_pad = atoi(e);
     if (const char *e = getenv("SEPFWI_RES_DEBUG")) h->res_dbg = atoi(e);
     if (const char *e = getenv("SEPFWI_RESIDENT_RPT")) h->res_forced_rpt = atoi(e);
     h->plan_debug = getenv("SEPFWI_PLAN_DEBUG") != nullptr;
     h->res_fake_refuse = getenv("SEPFWI_RES_FAKE_REFUSE") != nullptr;
-    if (const char *e = getenv("SEPFWI_MERGE_BWD")) h->merge_bwd = atoi(e) != 0;
     {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
@@ -380,10 +380,9 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     }
     if (h->stream) {
-        CU(cudaFuncSetAttribute(k_stream_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM));
-        CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
-        CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
-        CU(cudaFuncSetAttribute(k_stream_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AR_SMEM));
+        CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM + h->smem_pad));
+        CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM + h->smem_pad));
+        CU(cudaFuncSetAttribute(k_stream_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AR_SMEM + h->smem_pad));
     }
     h->resident = h->stream && pp->kernels == 0 && d.nPml <= RS_PW;
     if (const char *e = getenv("SEPFWI_RESIDENT")) h->resident = h->resident && atoi(e) != 0;
@@ -703,7 +702,7 @@ static int stage_batch(sepfwi_handle *h, int nb, const sepfwi_shot *shots, bool 
     CU(cudaMemcpyAsync(h->t_int, h->h_int, h->n_int * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->t_flt, h->h_flt, h->n_flt * sizeof(float), cudaMemcpyHostToDevice, st));
     h->staged_sig = sig;
-    for (int k = 0; k < 4; k++) h->plan_sig[k] = 0;      // the adjoint plan looks at the staged injection tables
+    for (int k = 0; k < 3; k++) h->plan_sig[k] = 0;      // the adjoint plan looks at the staged injection tables
     return 0;
 }
 
@@ -719,7 +718,7 @@ static int max_nrec(int nb, const sepfwi_shot *shots)
 //     CPML memory variables, no look-ahead): they get shorter chunks and are listed first so they never form the tail;
 //   * interior chunks are Lz rows with (Lz + 4) a multiple of the 6-row unroll, Lz chosen so that the item count fills whole
 //     waves of nSM x 8 resident warps (2 CTAs x 4 warps at 255 registers).  SEPFWI_LZ / SEPFWI_LZE override the two heights.
-static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 adj, 3 merged recon + adj*/, StreamArgs &sa, cudaStream_t st,
+static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 adj*/, StreamArgs &sa, cudaStream_t st,
                        std::vector<int4> *items_out = nullptr)
 {
     const Dims &d = h->d;
@@ -727,8 +726,8 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     const uint64_t want = h->staged_sig ? (h->staged_sig ^ ((uint64_t)nb << 48)) | 1ull : 0;
     if (!items_out && want && h->plan_sig[which] == want) { sa = h->plan_sa[which]; return 0; }
     memset(&sa, 0, sizeof(sa));
-    const int model = which == 3 ? 2 : which;            // the merged launch is planned with the adjoint sweep's costs ...
-    const double mult = which == 3 ? 2.0 : 1.0;           // ... and carries two warps per item
+    const int model = which;
+    const double mult = 1.0;
     const int nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
     // interior rows [zi0, zi1) / strips: the adjoint sweep keeps CPML memory on strips nPml + 2 wide (el_stress_adj.cu:67-72),
     // a warp recomputes a 2-cell halo, and the reverse sweep restores a ring that reaches 3 cells into the interior:
@@ -801,6 +800,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     std::stable_sort(inner.begin(), inner.end(), [&](const int4 &p, const int4 &q) {
         const int hp = heavy[p.x / SW_OWN] ? 0 : 1, hq = heavy[q.x / SW_OWN] ? 0 : 1;
         return hp != hq ? hp < hq : p.y < q.y; });
+    const int nEdgeItems = (int)edge.size();
     edge.insert(edge.end(), inner.begin(), inner.end());
     if (items_out) { *items_out = edge; return 0; }      // host-only planning (sepfwi_plan_stream): nothing is uploaded
     if (edge.size() > h->work_cap[which]) {
@@ -816,7 +816,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     } else if (h->plan_sig[which]) CU(cudaStreamSynchronize(st));      // the pinned mirror may still be in flight / the list in use
     memcpy(h->work_host[which], edge.data(), edge.size() * sizeof(int4));
     CU(cudaMemcpyAsync(h->work[which], h->work_host[which], edge.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-    sa.work = h->work[which]; sa.nWork = (int)edge.size();
+    sa.work = h->work[which]; sa.nWork = (int)edge.size(); sa.nEdge = nEdgeItems;
     h->plan_sa[which] = sa; h->plan_sig[which] = want;
     return 0;
 }
@@ -910,7 +910,7 @@ extern "C" int sepfwi_plan_resident(const sepfwi_params *pp, int nshots, int nsm
 // *n receives the number of items the plan has (may exceed cap).
 extern "C" int sepfwi_plan_stream(const sepfwi_params *pp, int nshots, int nsm, int which, int *items, int cap, int *n)
 {
-    if (!pp || !n || nshots < 1 || nsm < 1 || which < 0 || which > 3 || (cap > 0 && !items)) return fail(SEPFWI_EINVAL, "bad argument");
+    if (!pp || !n || nshots < 1 || nsm < 1 || which < 0 || which > 2 || (cap > 0 && !items)) return fail(SEPFWI_EINVAL, "bad argument");
     sepfwi_handle h;
     h.p = *pp;
     int rc = fill_dims(*pp, h.d);
@@ -1074,7 +1074,7 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
             const bool pr = it < h->prof_steps;
             sa.it = it; sa.mask = (it >= 1 && mrec > 0) ? mask : 0;
             cudaError_t le = cudaSuccess;
-            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (le = launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), FR_SMEM, st, h->pdl, a, sa)));
+            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (le = launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), FR_SMEM + h->smem_pad, st, h->pdl, a, sa)));
             CU(le);
         }
         const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state
@@ -1174,30 +1174,24 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     const int rx = d.x1 + 2 - (d.nPml - 2) + 1, rz = d.z1 + 2 - (d.nPml - 2) + 1;
     dim3 rgrd((rx + BX - 1) / BX, (rz + BY - 1) / BY, nb);
     dim3 igrd((minj + 127) / 128, nb);
-    StreamArgs sa, sr, sm;
+    StreamArgs sa, sr;
     if (h->stream) {
-        int rc;
-        if (h->merge_bwd) { rc = stream_plan(h, nb, 3, sm, st); if (rc) return rc; }
-        else { rc = stream_plan(h, nb, 2, sa, st); if (rc) return rc; rc = stream_plan(h, nb, 1, sr, st); if (rc) return rc; }
+        int rc = stream_plan(h, nb, 2, sa, st);
+        if (rc) return rc;
+        rc = stream_plan(h, nb, 1, sr, st);
+        if (rc) return rc;
     }
     CU(cudaEventRecord(h->ev[2], st));
     if (h->stream) {
         int q = (d.nSteps - 1) & 1, pa = 0;     // forward state nSteps-1 sits in buffer q; adjoint starts in buffer 0
-        const int nctas = (sm.nWork + SW_WPB - 1) / SW_WPB;
         for (int it = d.nSteps - 2; it >= 0; it--) {
             const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
             cudaError_t le = cudaSuccess;
-            if (h->merge_bwd) {
-                // one launch: CTA 0 writes the stf gradient, then CTA pairs (reconstruction, adjoint) over the same items
-                sm.it = it; sm.q = q; sm.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_BWD, pr, st, (le = launch_pdl(k_stream_bwd, dim3(1 + 2 * nctas, nb), dim3(SW_NT), BW_SMEM, st, h->pdl, a, sm)));
-            } else {
-                sr.it = it; sr.q = q; sr.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (le = launch_pdl(k_stream_recon, dim3((sr.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM, st, h->pdl, a, sr)));
-                CU(le);
-                sa.it = it; sa.q = q; sa.pa = pa;
-                LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (le = launch_pdl(k_stream_adj, dim3(1 + (sa.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), AR_SMEM, st, h->pdl, a, sa)));
-            }
+            sr.it = it; sr.q = q; sr.pa = pa;
+            LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (le = launch_pdl(k_stream_recon, dim3((sr.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM + h->smem_pad, st, h->pdl, a, sr)));
+            CU(le);
+            sa.it = it; sa.q = q; sa.pa = pa;
+            LAUNCH(h, SEPFWI_K_STREAM_ADJ, pr, st, (le = launch_pdl(k_stream_adj, dim3(1 + (sa.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), AR_SMEM + h->smem_pad, st, h->pdl, a, sa)));
             CU(le);
             q ^= 1; pa ^= 1;
         }

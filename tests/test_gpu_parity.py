@@ -149,20 +149,6 @@ def test_resident_forward_general_fiber_weights():
     _assert_same(_run_resident(prob, 2, weights=w), _run_both(prob, 1, weights=w), prob.nshots, tol_g=1e-4)
 
 
-@pytest.mark.parametrize("merge", ["0", "1"])
-def test_reverse_time_step_merged_and_separate_launches(merge, monkeypatch):
-    """The reverse-time step as one launch (reconstruction and adjoint CTAs side by side, the default) and as two launches
-    give the same gradient as the unfused baseline kernels -- and the same bits as each other (same per-item arithmetic)."""
-    monkeypatch.setenv("SEPFWI_MERGE_BWD", merge)
-    prob = problems.medium()
-    got = _run_both(prob, 3)
-    _assert_same(got, _run_both(prob, 1), prob.nshots)
-    monkeypatch.setenv("SEPFWI_MERGE_BWD", "1" if merge == "0" else "0")
-    other = _run_both(prob, 3)
-    for k in ("glam", "gmu", "grho"):
-        assert np.array_equal(got[1][k], other[1][k]), k
-
-
 def test_cpml_profiles_match_oracle():
     O, Propagator, _ = _mods()
     prob = problems.small()
