@@ -13,6 +13,7 @@
  *   sepfwi_forward_snapshots <- elasticSolver.forward_it(isrc, True)   DAS_Waveform_Modeling/src/elasticSolver.py:185-305
  *   sepfwi_gradient  <- cufd(calc_id = 0 / 1) shot loop         libCUFD.cu:170-724, 775-780
  *   sepfwi_ring_*    <- Bnd::field_from_bnd / field_to_bnd      Boundary.cu:55-101, utilities.cu:362-425
+ *   sepfwi_set_data_options <- if_win / filter / if_cross_misfit / if_src_update   Parameter.cpp:139-176, utilities.cu:733-1356
  *
  * Plain C: pointers, sizes and POD structs only -- no torch, no C++ types.  All
  * functions return 0 on success or a negative SEPFWI_E* code; sepfwi_last_error()
@@ -91,7 +92,26 @@ typedef struct sepfwi_shot {
     float *out[7];         /* forward: pr, vx, vz, ett, exx, ezz, exz traces [nrec][nSteps] (NULL = skip); space `mem`  */
     float *gstf;           /* gradient: HOST pointer, nSteps floats (NULL = skip)                                      */
     const float *weights;  /* optional HOST [nrec][3]: ett = w0*exx + w1*ezz + w2*exz (NULL = pure fiber component)    */
+    /* data-side options (sepfwi_set_data_options); all optional, HOST pointers */
+    const float *win_start;     /* [nrec] window start / end in seconds, survey_file.json "win_start" / "win_end" (Src_Rec.cu:145-170) */
+    const float *win_end;
+    const float *trace_weights; /* [nrec] "weights" (Src_Rec.cu:176-193); NULL = 1                                    */
+    float src_weight;           /* "src_weight" (Src_Rec.cu:195-201); 0 = unset = 1                                   */
+    float *src_updated;         /* out, if_src_update: nSteps samples of the updated source time function (NULL = skip) */
 } sepfwi_shot;
+
+/* Data-side operators applied to observed and synthetic DAS traces between the forward and the reverse-time loop, in the order of
+ * the (commented) call sites libCUFD.cu:353-457; the switches are those of para_file.json (Parameter.cpp:139-176).  All off (the
+ * default, and the reference's live behaviour): residual = obs - syn, misfit = 0.5 sum residual^2. */
+typedef struct sepfwi_data_options {
+    int   if_win;           /* per-trace windows + trace weights + source weight, cuda_window utilities.cu:790-842 (needs win_start / win_end) */
+    float win_ratio;        /* taper fraction of the window length; 0 = 0.005 (libCUFD.cu:63)                            */
+    int   if_filter;        /* band-pass, bp_filter1d utilities.cu:1115-1168                                             */
+    float filter[4];        /* corner frequencies f0 < f1 <= f2 < f3 in Hz ("filter" in para_file.json)                  */
+    int   if_cross_misfit;  /* normalised zero-lag cross-correlation misfit + its adjoint source, utilities.cu:1011-1113  */
+    int   if_src_update;    /* least-squares source-signature update of the synthetic data + residual, utilities.cu:1170-1356 */
+    int   reserved[6];
+} sepfwi_data_options;
 
 typedef struct sepfwi_handle sepfwi_handle;
 
@@ -100,6 +120,15 @@ int sepfwi_version(void);
 
 int sepfwi_create(const sepfwi_params *p, int device, sepfwi_handle **out);
 int sepfwi_destroy(sepfwi_handle *h);
+
+/* Select the data-side operators of later sepfwi_gradient calls (NULL = all off).  Allocates its scratch on the device. */
+int sepfwi_set_data_options(sepfwi_handle *h, const sepfwi_data_options *o);
+
+/* The data-side chain alone on given traces of one shot: obs, syn [nrec][nSteps] in space `mem` -> adjoint source `res`, conditioned
+ * synthetic `syn_out` (each may be NULL), the shot's misfit contribution (0.5 included); shot->src_updated receives the updated source
+ * when if_src_update is set.  Needs sepfwi_set_data_options with at least one switch on. */
+int sepfwi_condition(sepfwi_handle *h, const sepfwi_shot *shot, const float *obs, const float *syn, float *res, float *syn_out,
+                     double *misfit, int mem, void *stream);
 
 /* lambda, mu in MPa, rho in kg/m^3, row-major [nz][nx] (the tensors FWIFunction receives,
  * FWI_ops.py:46-51).  Sponge flavour: lambda, mu in Pa.  Computes the averaged

@@ -108,6 +108,8 @@ bool read_first_line(const std::string &fname, std::string &line)
 struct Cached {
     sepfwi_handle *h = nullptr;
     int maxrec = 0;
+    bool dopt_set = false;      // the handle currently carries data-side options ...
+    sepfwi_data_options dopt;   // ... these
     std::mutex use;
     ~Cached() { if (h) sepfwi_destroy(h); }
 };
@@ -170,7 +172,19 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
     if (!js.ok || survey.kind != JVal::Obj) return efail(SEPFWI_EIO, "survey file is not a JSON object");
 
     const int nS = (int)nSteps, npml = (int)nPml;
-    struct ShotData { std::vector<int> zr, xr; std::vector<float> obs, out[4], gstf, w; };
+    struct ShotData { std::vector<int> zr, xr; std::vector<float> obs, out[4], gstf, w, ws, we, wt; };
+    // data-side switches (Parameter.cpp:139-176)
+    sepfwi_data_options dopt;
+    memset(&dopt, 0, sizeof(dopt));
+    if (const JVal *v = para.get("if_win")) dopt.if_win = v->kind == JVal::Bool && v->b;
+    if (const JVal *v = para.get("if_src_update")) dopt.if_src_update = v->kind == JVal::Bool && v->b;
+    if (const JVal *v = para.get("if_cross_misfit")) dopt.if_cross_misfit = v->kind == JVal::Bool && v->b;
+    if (const JVal *v = para.get("filter")) {
+        if (v->kind != JVal::Arr || v->arr.size() < 4) return efail(SEPFWI_EIO, "filter must be an array of four frequencies");
+        dopt.if_filter = 1;
+        for (int k = 0; k < 4; k++) dopt.filter[k] = (float)v->arr[k].num;
+    }
+    const bool any_dopt = dopt.if_win || dopt.if_filter || dopt.if_cross_misfit || dopt.if_src_update;
     std::vector<ShotData> sd(group_size);
     std::vector<sepfwi_shot> shots(group_size);
     int maxrec = 1;
@@ -200,6 +214,20 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
             }
             sh.weights = sd[i].w.data();
         }
+        auto farr = [&](const char *k, std::vector<float> &dst) -> bool {
+            const JVal *a = s->get(k);
+            if (!a) return false;
+            if (a->kind != JVal::Arr || (int)a->arr.size() < nrec) return false;
+            dst.resize(nrec);
+            for (int r = 0; r < nrec; r++) dst[r] = (float)a->arr[r].num;
+            return true;
+        };
+        if (dopt.if_win) {                                                                                                     // Src_Rec.cu:145-170
+            if (!farr("win_start", sd[i].ws) || !farr("win_end", sd[i].we)) return efail(SEPFWI_EIO, key + ": if_win needs win_start and win_end (nrec entries)");
+            sh.win_start = sd[i].ws.data(); sh.win_end = sd[i].we.data();
+        }
+        if (farr("weights", sd[i].wt)) sh.trace_weights = sd[i].wt.data();                                                     // Src_Rec.cu:176-193
+        if (const JVal *sw = s->get("src_weight")) if (sw->kind == JVal::Num) sh.src_weight = (float)sw->num;                // Src_Rec.cu:195-201
         const JVal *rxz = s->get("src_rxz");
         sh.src_rxz = rxz && rxz->kind == JVal::Num ? (float)rxz->num : 1.0f;                                                     // RSXXZZ, utilities.h:21
         maxrec = nrec > maxrec ? nrec : maxrec;
@@ -260,6 +288,11 @@ extern "C" int sepfwi_cufd(float *misfit, float *grad_Lambda, float *grad_Mu, fl
 
     int rc = sepfwi_set_model(h, Lambda, Mu, Den, SEPFWI_MEM_HOST, nullptr);
     if (rc) return rc;
+    if (calc_id != 2 && (any_dopt != ent->dopt_set || (any_dopt && memcmp(&dopt, &ent->dopt, sizeof(dopt)) != 0))) {
+        rc = sepfwi_set_data_options(h, any_dopt ? &dopt : nullptr);      // only when the switches changed: it reallocates scratch
+        if (rc) return rc;
+        ent->dopt_set = any_dopt; ent->dopt = dopt;
+    }
 
     auto fname = [&](const char *comp, int id) { return dd->str + "/Shot_" + comp + std::to_string(id) + ".bin"; };
     static const char *comps[4] = {"pr", "vx", "vz", "ett"};

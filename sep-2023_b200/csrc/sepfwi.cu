@@ -20,6 +20,7 @@
 #include "kernels_base.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_resident.cuh"
+#include "kernels_data.cuh"
 
 using namespace sepfwi;
 
@@ -94,6 +95,13 @@ struct sepfwi_handle {
     float courant = 0.f;
     bool have_model = false;
     long long launches = 0;
+    // data-side operators (kernels_data.cuh): options, host-built tables, device scratch (allocated by sepfwi_set_data_options)
+    sepfwi_data_options dopt;
+    bool dopt_any = false;
+    int d_n2 = 0, d_nfft = 0, d_k0 = 0, d_nband = 0;   // padded length 2 nt, bins of the full spectrum, band-pass bins [k0, k0 + nband)
+    float2 *d_tw = nullptr, *d_F[2] = {nullptr, nullptr}, *d_Fs = nullptr, *d_coef = nullptr;
+    float *d_gain = nullptr, *d_nf = nullptr, *d_win = nullptr, *d_ratio = nullptr, *d_src = nullptr, *h_win = nullptr, *h_src = nullptr;
+    unsigned *d_mx = nullptr;
     double *hj = nullptr; float *hg = nullptr;       // pinned staging: per-shot misfits, stf gradients
     size_t hj_cap = 0, hg_cap = 0;
     double last_misfit = 0.0;                        // misfit of the last sepfwi_gradient call in double precision
@@ -274,10 +282,22 @@ static KArgs kargs(const sepfwi_handle *h)
     return a;
 }
 
+static void free_data_scratch(sepfwi_handle *h)
+{
+    void *dp[] = {h->d_tw, h->d_F[0], h->d_F[1], h->d_Fs, h->d_coef, h->d_gain, h->d_nf, h->d_win, h->d_ratio, h->d_src, h->d_mx};
+    for (void *q : dp) if (q) cudaFree(q);
+    h->d_tw = nullptr; h->d_F[0] = h->d_F[1] = nullptr; h->d_Fs = h->d_coef = nullptr;
+    h->d_gain = h->d_nf = h->d_win = h->d_ratio = h->d_src = nullptr; h->d_mx = nullptr;
+    if (h->h_win) cudaFreeHost(h->h_win);
+    if (h->h_src) cudaFreeHost(h->h_src);
+    h->h_win = h->h_src = nullptr;
+}
+
 extern "C" int sepfwi_destroy(sepfwi_handle *h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    free_data_scratch(h);
     float *fp[] = {h->state, h->model, h->cz, h->cx, h->cxs, h->cxv, h->cxa, h->damp, h->ring, h->trace, h->grad, h->gstf,
                    h->dense[0], h->dense[1], h->dense[2], h->t_flt};
     for (float *q : fp) if (q) cudaFree(q);
@@ -312,6 +332,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     sepfwi_handle *h = new sepfwi_handle();
     for (int i = 0; i < 4; i++) h->ev[i] = nullptr;
     h->p = *pp; h->device = device;
+    memset(&h->dopt, 0, sizeof(h->dopt));
     h->sponge = pp->flavour == SEPFWI_FLAVOUR_SPONGE;
     int rc = fill_dims(*pp, h->d);
     if (rc) { delete h; return rc; }
@@ -1160,6 +1181,184 @@ extern "C" int sepfwi_forward_snapshots(sepfwi_handle *h, const sepfwi_shot *sho
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Data-side operators (kernels_data.cuh): options + scratch, and the per-shot chain of libCUFD.cu:353-457.
+extern "C" int sepfwi_set_data_options(sepfwi_handle *h, const sepfwi_data_options *o)
+{
+    if (!h) return fail(SEPFWI_EINVAL, "null handle");
+    if (h->sponge) return fail(SEPFWI_EINVAL, "the sponge flavour is forward-only");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    free_data_scratch(h);
+    memset(&h->dopt, 0, sizeof(h->dopt));
+    h->dopt_any = false;
+    if (!o) return 0;
+    sepfwi_data_options q = *o;
+    if (q.win_ratio <= 0.f) q.win_ratio = 0.005f;                        // libCUFD.cu:63
+    if (q.win_ratio > 0.5f) return fail(SEPFWI_EINVAL, "win_ratio must not exceed 0.5 (utilities.cu:803-806)");
+    if (q.if_filter && !(q.filter[0] >= 0.f && q.filter[0] < q.filter[1] && q.filter[1] <= q.filter[2] && q.filter[2] < q.filter[3]))
+        return fail(SEPFWI_EINVAL, "filter needs corner frequencies 0 <= f0 < f1 <= f2 < f3");
+    h->dopt = q;
+    h->dopt_any = q.if_win || q.if_filter || q.if_cross_misfit || q.if_src_update;
+    if (!h->dopt_any) return 0;
+    const Dims &d = h->d;
+    const int nt = d.nSteps, n2 = 2 * nt, nfft = n2 / 2 + 1;
+    h->d_n2 = n2; h->d_nfft = nfft;
+    // twiddles (cos, sin)(2 pi j / n2) in double precision
+    std::vector<float2> tw(n2);
+    for (int j = 0; j < n2; j++) { const double th = 2.0 * M_PI * (double)j / (double)n2; tw[j] = make_float2((float)cos(th), (float)sin(th)); }
+    // band-pass gain per bin, cuda_bp_filter1d (utilities.cu:733-765) in its float arithmetic; the band = the bins it leaves non-zero
+    std::vector<float> gain;
+    h->d_k0 = 0; h->d_nband = 0;
+    if (q.if_filter) {
+        const float PI = 3.141592653589793238462643383279502884197169f;
+        const float df = (float)(1.0 / h->p.dt / n2);
+        int kmin = nfft, kmax = -1;
+        std::vector<float> g(nfft, 0.f);
+        for (int k = 0; k < nfft; k++) {
+            const float freq = k * df;
+            float a;
+            if (freq >= q.filter[0] && freq < q.filter[1]) a = (float)sin(PI / 2.0 * (freq - q.filter[0]) / (q.filter[1] - q.filter[0]));
+            else if (freq >= q.filter[1] && freq < q.filter[2]) a = 1.0f;
+            else if (freq >= q.filter[2] && freq < q.filter[3]) a = (float)cos(PI / 2.0 * (freq - q.filter[2]) / (q.filter[3] - q.filter[2]));
+            else a = 0.0f;
+            g[k] = a * a;
+            if (g[k] != 0.f) { kmin = std::min(kmin, k); kmax = std::max(kmax, k); }
+        }
+        if (kmax < kmin) return fail(SEPFWI_EINVAL, "the band-pass leaves no frequency bin (df = %g Hz)", df);
+        h->d_k0 = kmin; h->d_nband = kmax - kmin + 1;
+        gain.assign(g.begin() + kmin, g.begin() + kmax + 1);
+    }
+    const size_t nbins_buf = q.if_src_update ? (size_t)nfft : (size_t)std::max(h->d_nband, 1);
+    auto dalloc = [&](void **ptr, size_t bytes) { return cudaMalloc(ptr, bytes) == cudaSuccess; };
+    bool ok = dalloc((void **)&h->d_tw, (size_t)n2 * sizeof(float2)) && dalloc((void **)&h->d_F[0], (size_t)d.maxRec * nbins_buf * sizeof(float2)) &&
+              dalloc((void **)&h->d_nf, (size_t)3 * d.maxRec * sizeof(float)) && dalloc((void **)&h->d_win, (size_t)3 * d.maxRec * sizeof(float)) &&
+              dalloc((void **)&h->d_ratio, sizeof(float)) && dalloc((void **)&h->d_mx, 2 * sizeof(unsigned)) &&
+              dalloc((void **)&h->d_src, (size_t)h->B * nt * sizeof(float)) && dalloc((void **)&h->d_gain, (size_t)std::max(h->d_nband, 1) * sizeof(float));
+    if (ok && q.if_src_update)
+        ok = dalloc((void **)&h->d_F[1], (size_t)d.maxRec * nfft * sizeof(float2)) && dalloc((void **)&h->d_Fs, (size_t)nfft * sizeof(float2)) &&
+             dalloc((void **)&h->d_coef, (size_t)nfft * sizeof(float2));
+    if (ok) ok = cudaMallocHost((void **)&h->h_win, (size_t)3 * d.maxRec * h->B * sizeof(float)) == cudaSuccess &&
+                 cudaMallocHost((void **)&h->h_src, (size_t)h->B * nt * sizeof(float)) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); free_data_scratch(h); h->dopt_any = false; return fail(SEPFWI_ENOMEM, "device scratch of the data-side operators"); }
+    CU(cudaMemcpy(h->d_tw, tw.data(), (size_t)n2 * sizeof(float2), cudaMemcpyHostToDevice));
+    if (q.if_filter) CU(cudaMemcpy(h->d_gain, gain.data(), gain.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// band-pass of ntr traces in place: forward transform at the band's bins, gain, inverse (bp_filter1d, utilities.cu:1115-1168)
+static void band_pass(sepfwi_handle *h, float *data, int ntr, cudaStream_t st)
+{
+    const int nt = h->d.nSteps;
+    k_dft_fwd<<<dim3((h->d_nband + DF_NT - 1) / DF_NT, ntr), DF_NT, 0, st>>>(data, nt, h->d_n2, 0, h->d_k0, h->d_nband, h->d_tw, h->d_F[0]);
+    k_dft_inv<<<dim3((nt + DF_NT - 1) / DF_NT, ntr), DF_NT, 0, st>>>(h->d_F[0], h->d_nband, h->d_k0, nullptr, h->d_gain, h->d_n2, h->d_tw,
+                                                                     1.0f / (float)h->d_n2, nullptr, data, nt);
+    h->launches += 2;
+}
+
+// Conditioned residual + misfit of slot s (shot sh): libCUFD.cu:353-457 on the DAS traces.  obs / cal are modified in place.
+static int run_conditioning(sepfwi_handle *h, int s, const sepfwi_shot &sh, cudaStream_t st)
+{
+    const Dims &d = h->d;
+    const sepfwi_data_options &o = h->dopt;
+    const int nt = d.nSteps, ntr = sh.nrec, n2 = h->d_n2, nfft = h->d_nfft;
+    const size_t cs = (size_t)d.maxRec * d.nSteps;
+    float *tb = h->trace + (size_t)s * d.nTrace * cs;
+    float *obs = tb + T_OBS * cs, *cal = tb + T_ETT * cs, *res = tb + T_RES * cs;
+    double *part = h->partial + (size_t)s * sepfwi_handle::NBLK_RES, *mis = h->misfit + s;
+    if (ntr <= 0) { CU(cudaMemsetAsync(mis, 0, sizeof(double), st)); return 0; }
+    const float srcw = sh.src_weight != 0.f ? sh.src_weight : 1.0f;
+    const dim3 gt((nt + 255) / 256, ntr);
+    float *wst = h->d_win, *wen = h->d_win + d.maxRec, *wwt = h->d_win + 2 * (size_t)d.maxRec;
+    if (o.if_win || o.if_cross_misfit) {
+        // windows and trace weights of this shot: pinned staging row of the slot, one asynchronous copy
+        if (o.if_win && (!sh.win_start || !sh.win_end)) return fail(SEPFWI_EINVAL, "if_win needs win_start / win_end of every shot");
+        float *hw = h->h_win + (size_t)s * 3 * d.maxRec;
+        for (int r = 0; r < ntr; r++) {
+            hw[r] = sh.win_start ? sh.win_start[r] : 0.f; hw[d.maxRec + r] = sh.win_end ? sh.win_end[r] : 0.f;
+            hw[2 * (size_t)d.maxRec + r] = sh.trace_weights ? sh.trace_weights[r] : 1.0f;
+        }
+        CU(cudaMemcpyAsync(h->d_win, hw, (size_t)3 * d.maxRec * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (o.if_win) {                                                   // :353-363
+        k_win_traces<<<gt, 256, 0, st>>>(obs, ntr, nt, h->p.dt, wst, wen, wwt, srcw, o.win_ratio);
+        k_win_traces<<<gt, 256, 0, st>>>(cal, ntr, nt, h->p.dt, wst, wen, wwt, srcw, o.win_ratio);
+        h->launches += 2;
+    }
+    if (o.if_filter) { band_pass(h, obs, ntr, st); band_pass(h, cal, ntr, st); }                    // :370-373
+    if (o.if_cross_misfit) { k_normfacts<<<ntr, 256, 0, st>>>(obs, cal, nt, h->d_nf, ntr); h->launches++; }   // :376-384
+    if (o.if_src_update) {                                            // :387-394, source_update utilities.cu:1170-1276
+        const dim3 gf((nfft + DF_NT - 1) / DF_NT, ntr), gi((nt + DF_NT - 1) / DF_NT, ntr);
+        const float *amp = h->t_flt + h->o_amp + (size_t)s * d.nSteps;      // tapered source, scaled by 1500^2 dt (linear: undone on output)
+        k_dft_fwd<<<gf, DF_NT, 0, st>>>(obs, nt, n2, 1, 0, nfft, h->d_tw, h->d_F[0]);
+        k_dft_fwd<<<gf, DF_NT, 0, st>>>(cal, nt, n2, 1, 0, nfft, h->d_tw, h->d_F[1]);
+        k_dft_fwd<<<dim3(gf.x, 1), DF_NT, 0, st>>>(amp, nt, n2, 0, 0, nfft, h->d_tw, h->d_Fs);
+        k_spectrum_coef<<<nfft, 256, 0, st>>>(h->d_F[0], h->d_F[1], ntr, nfft, h->d_Fs, h->d_coef);
+        k_dft_inv<<<gi, DF_NT, 0, st>>>(h->d_F[1], nfft, 0, h->d_coef, nullptr, n2, h->d_tw, 1.0f / (float)n2, nullptr, cal, nt);
+        float *srcn = h->d_src + (size_t)s * nt;
+        k_dft_inv<<<dim3(gi.x, 1), DF_NT, 0, st>>>(h->d_Fs, nfft, 0, nullptr, nullptr, n2, h->d_tw, 1.0f / (float)n2, nullptr, srcn, nt);
+        const float unscale = (float)(1.0 / (pow(1500.0, 2) * (double)h->p.dt));
+        k_scale_copy<<<(nt + 255) / 256, 256, 0, st>>>(srcn, srcn, nt, unscale);
+        CU(cudaMemsetAsync(h->d_mx, 0, 2 * sizeof(unsigned), st));
+        k_absmax2<<<64, 256, 0, st>>>(obs, cal, (size_t)ntr * nt, h->d_mx);        // amp_ratio_comp :1328-1356 (trace rows are contiguous)
+        k_amp_ratio<<<1, 1, 0, st>>>(h->d_mx, h->d_ratio);
+        h->launches += 9;
+    }
+    if (!o.if_cross_misfit) {                                         // :397-400
+        k_residual_one<<<sepfwi_handle::NBLK_RES, 256, 0, st>>>(obs, cal, res, ntr, nt, part);
+        k_sum_partials_one<<<1, 32, 0, st>>>(part, sepfwi_handle::NBLK_RES, mis);
+    } else {                                                          // :401-407
+        CU(cudaMemsetAsync(res, 0, (size_t)ntr * nt * sizeof(float), st));
+        k_cross_misfit<<<1, 256, 0, st>>>(h->d_nf, ntr, wwt, srcw, mis);
+    }
+    h->launches += 2;
+    if (o.if_src_update) {                                            // :430-433, source_update_adj utilities.cu:1280-1326
+        k_dft_fwd<<<dim3((nfft + DF_NT - 1) / DF_NT, ntr), DF_NT, 0, st>>>(res, nt, n2, 1, 0, nfft, h->d_tw, h->d_F[0]);
+        k_dft_inv<<<dim3((nt + DF_NT - 1) / DF_NT, ntr), DF_NT, 0, st>>>(h->d_F[0], nfft, 0, h->d_coef, nullptr, n2, h->d_tw, 1.0f / (float)n2,
+                                                                         h->d_ratio, res, nt);
+        h->launches += 2;
+    }
+    if (o.if_cross_misfit) { k_cross_adjoint<<<gt, 256, 0, st>>>(obs, cal, h->d_nf, ntr, nt, wwt, srcw, res); h->launches++; }   // :436-443
+    if (o.if_filter) band_pass(h, res, ntr, st);                      // :446-448
+    if (o.if_win) { k_win_traces<<<gt, 256, 0, st>>>(res, ntr, nt, h->p.dt, wst, wen, wwt, srcw, o.win_ratio); h->launches++; }   // :450-457
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// The data-side chain on given traces of ONE shot (no wave propagation): obs and syn [nrec][nSteps] in space `mem`; outputs (each may be
+// NULL) the adjoint source `res`, the conditioned synthetic `syn_out`, the shot's misfit contribution (already times 0.5) and -- through
+// shot->src_updated -- the updated source.  Uses slot 0 of the handle.
+extern "C" int sepfwi_condition(sepfwi_handle *h, const sepfwi_shot *shot, const float *obs, const float *syn, float *res, float *syn_out,
+                                double *misfit, int mem, void *stream)
+{
+    if (!h || !shot || !obs || !syn) return fail(SEPFWI_EINVAL, "null argument");
+    if (h->sponge) return fail(SEPFWI_EINVAL, "the sponge flavour is forward-only");
+    if (!h->dopt_any) return fail(SEPFWI_EINVAL, "no data-side option is set (sepfwi_set_data_options)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims &d = h->d;
+    int rc = stage_batch(h, 1, shot, false, st);
+    if (rc) return rc;
+    const size_t cs = (size_t)d.maxRec * d.nSteps, n = (size_t)shot->nrec * d.nSteps * sizeof(float);
+    const cudaMemcpyKind kin = mem == SEPFWI_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind kout = mem == SEPFWI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (n) {
+        CU(cudaMemcpyAsync(h->trace + T_OBS * cs, obs, n, kin, st));
+        CU(cudaMemcpyAsync(h->trace + T_ETT * cs, syn, n, kin, st));
+    }
+    rc = run_conditioning(h, 0, *shot, st);
+    if (rc) return rc;
+    if (n && res) CU(cudaMemcpyAsync(res, h->trace + T_RES * cs, n, kout, st));
+    if (n && syn_out) CU(cudaMemcpyAsync(syn_out, h->trace + T_ETT * cs, n, kout, st));
+    double J = 0.0;
+    CU(cudaMemcpyAsync(&J, h->misfit, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h->dopt.if_src_update && shot->src_updated)
+        CU(cudaMemcpyAsync(shot->src_updated, h->d_src, (size_t)d.nSteps * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (misfit) *misfit = 0.5 * J;
+    return 0;
+}
+
 // Backward time loop of one batch, libCUFD.cu:500-653.
 static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
 {
@@ -1261,16 +1460,27 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
                                    (size_t)sh.nrec * d.nSteps * sizeof(float), kin, st));
             }
         }
-        KArgs a = kargs(h);
-        k_residual<<<dim3(sepfwi_handle::NBLK_RES, nb), 256, 0, st>>>(a, h->partial, sepfwi_handle::NBLK_RES);
-        k_sum_partials<<<1, 32 * ((nb + 31) / 32), 0, st>>>(h->partial, sepfwi_handle::NBLK_RES, h->misfit, nb);
-        h->launches += 2;
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(h->hj + s0, h->misfit, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        // the synthetic traces leave before the data-side operators modify them in place
         for (int s = 0; s < nb; s++)
             if (shots[s0 + s].out[T_ETT] && shots[s0 + s].nrec > 0)
                 CU(cudaMemcpyAsync(shots[s0 + s].out[T_ETT], h->trace + ((size_t)s * d.nTrace + T_ETT) * cs,
                                    (size_t)shots[s0 + s].nrec * d.nSteps * sizeof(float), kout, st));
+        KArgs a = kargs(h);
+        if (!h->dopt_any) {
+            k_residual<<<dim3(sepfwi_handle::NBLK_RES, nb), 256, 0, st>>>(a, h->partial, sepfwi_handle::NBLK_RES);
+            k_sum_partials<<<1, 32 * ((nb + 31) / 32), 0, st>>>(h->partial, sepfwi_handle::NBLK_RES, h->misfit, nb);
+            h->launches += 2;
+        } else {
+            // shot by shot (the spectra scratch and the window table are shared by the slots; stream order keeps them apart)
+            for (int s = 0; s < nb; s++) {
+                rc = run_conditioning(h, s, shots[s0 + s], st);
+                if (rc) return rc;
+            }
+            if (h->dopt.if_src_update)
+                CU(cudaMemcpyAsync(h->h_src, h->d_src, (size_t)nb * d.nSteps * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h->hj + s0, h->misfit, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (with_adj) {
             int minj = 0;
             for (int s = 0; s < nb; s++) minj = std::max(minj, h->h_int[h->o_injN + s]);
@@ -1278,6 +1488,12 @@ extern "C" int sepfwi_gradient(sepfwi_handle *h, int nshots, const sepfwi_shot *
             if (rc) return rc;
             // one asynchronous copy of the batch's stf gradients into pinned staging (handed out after the final sync)
             CU(cudaMemcpyAsync(h->hg + (size_t)s0 * d.nSteps, h->gstf, (size_t)nb * d.nSteps * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        if (h->dopt_any && h->dopt.if_src_update) {
+            // updated source time functions of this batch: handed out per batch (the staging rows are reused)
+            CU(cudaStreamSynchronize(st));
+            for (int s = 0; s < nb; s++)
+                if (shots[s0 + s].src_updated) memcpy(shots[s0 + s].src_updated, h->h_src + (size_t)s * d.nSteps, (size_t)d.nSteps * sizeof(float));
         }
         if (timing || s0 + h->B >= nshots) {
             // the last batch is followed by the gradient reduction below: no sync here unless timing needs the events

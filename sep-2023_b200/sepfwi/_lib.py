@@ -29,7 +29,15 @@ class Shot(C.Structure):
     _fields_ = [("zs", C.c_int), ("xs", C.c_int), ("nrec", C.c_int),
                 ("zrec", C.c_void_p), ("xrec", C.c_void_p), ("stf", C.c_void_p),
                 ("src_rxz", C.c_float), ("obs_ett", C.c_void_p), ("out", C.c_void_p * 7),
-                ("gstf", C.c_void_p), ("weights", C.c_void_p)]
+                ("gstf", C.c_void_p), ("weights", C.c_void_p),
+                ("win_start", C.c_void_p), ("win_end", C.c_void_p), ("trace_weights", C.c_void_p),
+                ("src_weight", C.c_float), ("src_updated", C.c_void_p)]
+
+
+class DataOptions(C.Structure):
+    """sepfwi_data_options (include/sepfwi.h): the data-side switches of para_file.json."""
+    _fields_ = [("if_win", C.c_int), ("win_ratio", C.c_float), ("if_filter", C.c_int), ("filter", C.c_float * 4),
+                ("if_cross_misfit", C.c_int), ("if_src_update", C.c_int), ("reserved", C.c_int * 6)]
 
 
 # every symbol include/sepfwi.h declares (tests check the export list against the header)
@@ -38,7 +46,7 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
            "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots", "sepfwi_plan_resident", "sepfwi_plan_stream",
-           "sepfwi_last_misfit", "sepfwi_bytes_per_slot"]
+           "sepfwi_last_misfit", "sepfwi_bytes_per_slot", "sepfwi_set_data_options", "sepfwi_condition"]
 NKERNEL = 13
 
 _lib = None
@@ -80,6 +88,9 @@ def lib():
         L.sepfwi_resident_launches.argtypes = [C.c_void_p]
         L.sepfwi_resident_launches.restype = C.c_longlong
         L.sepfwi_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.sepfwi_set_data_options.argtypes = [C.c_void_p, C.POINTER(DataOptions)]
+        L.sepfwi_condition.argtypes = [C.c_void_p, C.POINTER(Shot), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
+                                       C.c_int, C.c_void_p]
         L.sepfwi_last_misfit.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.sepfwi_bytes_per_slot.argtypes = [C.POINTER(Params)]
         L.sepfwi_bytes_per_slot.restype = C.c_longlong

@@ -37,7 +37,8 @@ def _as_i32(a):
 class ShotSpec(object):
     """One shot in padded-grid indices (survey index + nPml, Src_Rec.cu:87-115)."""
 
-    def __init__(self, zs, xs, zrec, xrec, stf, src_rxz=1.0, weights=None):
+    def __init__(self, zs, xs, zrec, xrec, stf, src_rxz=1.0, weights=None, win_start=None, win_end=None, trace_weights=None,
+                 src_weight=1.0):
         self.zs, self.xs = int(zs), int(xs)
         self.zrec, self.xrec = _as_i32(zrec), _as_i32(xrec)
         if self.zrec.shape != self.xrec.shape or self.zrec.ndim != 1:
@@ -47,6 +48,14 @@ class ShotSpec(object):
         self.weights = None if weights is None else _as_f32_host(weights).reshape(-1, 3)
         if self.weights is not None and self.weights.shape[0] != self.zrec.size:
             raise ValueError("weights must be (nrec, 3)")
+        # data-side options (Propagator.set_data_options): per-trace windows [s], trace weights, source weight
+        self.win_start = None if win_start is None else _as_f32_host(win_start).reshape(-1)
+        self.win_end = None if win_end is None else _as_f32_host(win_end).reshape(-1)
+        self.trace_weights = None if trace_weights is None else _as_f32_host(trace_weights).reshape(-1)
+        for a in (self.win_start, self.win_end, self.trace_weights):
+            if a is not None and a.size != self.zrec.size:
+                raise ValueError("win_start / win_end / trace_weights need one entry per receiver")
+        self.src_weight = float(src_weight)
 
     @property
     def nrec(self):
@@ -121,6 +130,19 @@ class Propagator(object):
         check(lib().sepfwi_set_model(self._h, ptrs[0][0], ptrs[1][0], ptrs[2][0],
                                      _lib.MEM_DEVICE if dev[0] else _lib.MEM_HOST, self._stream()))
 
+    def set_data_options(self, if_win=False, win_ratio=0.0, filter=None, if_cross_misfit=False, if_src_update=False):
+        """Data-side operators of later gradient() calls -- the switches of para_file.json (`if_win`, `filter` = [f0, f1, f2, f3] Hz,
+        `if_cross_misfit`, `if_src_update`; Src/Parameter.cpp:139-176).  All off restores residual = obs - syn."""
+        o = _lib.DataOptions()
+        o.if_win, o.win_ratio = (1 if if_win else 0), float(win_ratio)
+        if filter is not None:
+            o.if_filter = 1
+            for k in range(4):
+                o.filter[k] = float(filter[k])
+        o.if_cross_misfit, o.if_src_update = (1 if if_cross_misfit else 0), (1 if if_src_update else 0)
+        check(lib().sepfwi_set_data_options(self._h, C.byref(o)))
+        self._src_update = bool(if_src_update)
+
     @property
     def courant(self):
         c = C.c_float()
@@ -189,6 +211,11 @@ class Propagator(object):
             c.src_rxz = s.src_rxz
             if s.weights is not None:
                 c.weights = s.weights.ctypes.data
+            for name in ("win_start", "win_end", "trace_weights"):
+                a = getattr(s, name, None)
+                if a is not None:
+                    setattr(c, name, a.ctypes.data)
+            c.src_weight = getattr(s, "src_weight", 1.0)
             keep.append(s)
         return arr
 
@@ -235,6 +262,22 @@ class Propagator(object):
         check(lib().sepfwi_forward_snapshots(self._h, arr, int(save_step), snaps.ctypes.data, _lib.MEM_HOST, self._stream()))
         return d, snaps
 
+    def condition(self, shot, obs, syn):
+        """The data-side chain alone (no propagation) on host traces [nrec, nSteps] of one shot.
+        Returns dict(res, syn, misfit, src_updated)."""
+        keep = []
+        arr = self._shot_array([shot], keep)
+        o, s = _as_f32_host(obs), _as_f32_host(syn)
+        if o.shape != (shot.nrec, self.nSteps) or s.shape != o.shape:
+            raise ValueError("obs and syn must have shape (%d, %d)" % (shot.nrec, self.nSteps))
+        res, out = np.zeros_like(o), np.zeros_like(o)
+        upd = np.zeros(self.nSteps, np.float32)
+        arr[0].src_updated = upd.ctypes.data
+        J = C.c_double(0.0)
+        check(lib().sepfwi_condition(self._h, arr, o.ctypes.data, s.ctypes.data, res.ctypes.data, out.ctypes.data, C.byref(J),
+                                     _lib.MEM_HOST, self._stream()))
+        return dict(res=res, syn=out, misfit=J.value, src_updated=upd)
+
     def gradient(self, shots, obs, with_adj=True, device=False, want_syn=False, grad_out=None):
         """Misfit and gradient of `shots` against observed DAS data `obs` (list of [nrec, nSteps]).
         device=True: obs are CUDA tensors and the gradients are returned as CUDA tensors.
@@ -243,7 +286,7 @@ class Propagator(object):
         Returns dict(misfit, misfit64, glam, gmu, grho, gstf[list], syn[list])."""
         keep = []
         arr = self._shot_array(shots, keep)
-        gstf, syn = [], []
+        gstf, syn, src_upd = [], [], []
         for k, s in enumerate(shots):
             p, is_dev = self._ptr(obs[k], keep)
             if is_dev != bool(device):
@@ -255,6 +298,10 @@ class Propagator(object):
                 g = np.zeros(self.nSteps, np.float32)
                 arr[k].gstf = g.ctypes.data
                 gstf.append(g)
+            if getattr(self, "_src_update", False):
+                u = np.zeros(self.nSteps, np.float32)
+                arr[k].src_updated = u.ctypes.data
+                src_upd.append(u)
             if want_syn:
                 if device:
                     import torch
@@ -288,4 +335,5 @@ class Propagator(object):
                                     self._stream()))
         m64 = C.c_double(0.0)
         check(lib().sepfwi_last_misfit(self._h, C.byref(m64)))
-        return dict(misfit=misfit.value, misfit64=m64.value, glam=g3[0], gmu=g3[1], grho=g3[2], gstf=gstf, syn=syn)
+        return dict(misfit=misfit.value, misfit64=m64.value, glam=g3[0], gmu=g3[1], grho=g3[2], gstf=gstf, syn=syn,
+                    src_updated=src_upd)

@@ -90,8 +90,16 @@ def _shots(para, shot_ids, Stf):
     stf = Stf.detach().cpu().numpy() if isinstance(Stf, torch.Tensor) else np.asarray(Stf)
     stf = np.ascontiguousarray(stf, np.float32)
     sv = fwi_utils.load_survey(para["survey_fname"], shot_ids, para["nPoints_pml"])
-    return [ShotSpec(s["zs"], s["xs"], s["zrec"], s["xrec"], stf[int(sid)], s["src_rxz"], weights=s.get("weights"))
+    return [ShotSpec(s["zs"], s["xs"], s["zrec"], s["xrec"], stf[int(sid)], s["src_rxz"], weights=s.get("weights"),
+                     win_start=s.get("win_start"), win_end=s.get("win_end"), trace_weights=s.get("trace_weights"),
+                     src_weight=s.get("src_weight", 1.0))
             for s, sid in zip(sv, shot_ids)], stf.shape
+
+
+def _data_options(para):
+    """The data-side switches of para_file.json (Src/Parameter.cpp:139-176) as Propagator.set_data_options keywords."""
+    return dict(if_win=bool(para.get("if_win", False)), filter=para.get("filter"),
+                if_cross_misfit=bool(para.get("if_cross_misfit", False)), if_src_update=bool(para.get("if_src_update", False)))
 
 
 _OBS_CAP_BYTES = 64 << 30      # device bytes the observed-data cache may hold per process (least recently used goes first)
@@ -166,6 +174,10 @@ def _gradient_on_device(device, Lambda, Mu, Den, Stf, ids, para, with_adj, packe
         P = _prop(para, device, with_adj, nrec, len(ids))
         lam, mu, den = _model_on(device, Lambda, Mu, Den)
         P.set_model(lam, mu, den)
+        opts = _data_options(para)
+        if getattr(P, "_data_opts", None) != opts and (any(v for v in opts.values()) or getattr(P, "_data_opts", None) is not None):
+            P.set_data_options(**opts)
+            P._data_opts = opts
         obs = [_obs(para, sid, s.nrec, device) for sid, s in zip(ids, shots)]
         if packed:
             pk = dist.packed_for((para["nz"], para["nx"]), stf_shape, "cuda:%d" % device)

@@ -114,7 +114,7 @@ def read_json_first_line(fname):
 
 def load_survey(survey_fname, shot_ids, nPml):
     """Parse survey_file.json for `shot_ids` the way Src_Rec does (Src/Src_Rec.cu:74-120):
-    +nPml on every index.  Returns a list of dict(zs, xs, zrec, xrec, src_rxz, weights)."""
+    +nPml on every index.  Returns a list of dict(zs, xs, zrec, xrec, src_rxz, weights, win_start, win_end, trace_weights, src_weight)."""
     js = read_json_first_line(survey_fname)
     out = []
     for sid in shot_ids:
@@ -125,5 +125,10 @@ def load_survey(survey_fname, shot_ids, nPml):
                         xrec=np.asarray(s['x_rec'][:n], np.int32) + nPml,
                         src_rxz=float(s.get('src_rxz', 1.0)),
                         weights=(np.asarray(s['das_sensitivity'], np.float32).reshape(n, 3)
-                                 if 'das_sensitivity' in s else None)))
+                                 if 'das_sensitivity' in s else None),
+                        # data-side options (Src_Rec.cu:145-201): windows in seconds, trace weights, source weight
+                        win_start=(np.asarray(s['win_start'][:n], np.float32) if 'win_start' in s else None),
+                        win_end=(np.asarray(s['win_end'][:n], np.float32) if 'win_end' in s else None),
+                        trace_weights=(np.asarray(s['weights'][:n], np.float32) if 'weights' in s else None),
+                        src_weight=float(s.get('src_weight', 1.0))))
     return out

@@ -294,3 +294,94 @@ def test_one_process_per_gpu_nccl_matches_single_process(tmp_path):
     assert len(one) == 3 and len(two) == 3
     # the sum over shots is associated differently (per-rank partial sums), so agreement is to rounding, not bit-exact
     assert np.allclose(one, two, rtol=2e-5), (one, two)
+
+
+# ---------------------------------------------------------------------------------------------
+# every parameterisation module, driven through the op with CUDA tensors
+@pytest.mark.parametrize("kind,f0,g0", [("002", 1.08179e4, 1.68776), ("003", 3.52002e4, 4.02957)])
+def test_reference_notebook_iterate0_lame_and_impedance_modules_on_cuda(tmp_path, kind, f0, g0):
+    """The reference's other two published logs: notebooks 002 (FWI_Lame_Den) and 003 (FWI_IP_IS_Den),
+        At iterate 0  f = 1.08179D+04 |proj g| = 1.68776   /   f = 3.52002D+04 |proj g| = 4.02957
+    with the model, the source and the shot ids living on the GPU: f(x0) to the 6 printed digits; |proj g| carries the
+    reference's residual-injection race (181 adjacent receivers) and is only bracketed."""
+    import torch
+    from sepfwi import drivers, fwi_ops
+    prob = drivers.anomaly_problem(kind)
+    prob.stf = prob.stf.cuda()
+    vals = {}
+    for compat in (True, False):
+        files = drivers.write_files(prob, str(tmp_path / ("c%d" % compat)), ref_race_compat=compat or None)
+        drivers.generate_data(prob, files, device="cuda")
+        fwi = drivers.build_fwi(prob, files, device="cuda")
+        loss = fwi(prob.shot_ids, ngpu=1)
+        loss.backward()
+        grads = [getattr(fwi, n).grad for n in fwi.NAMES]
+        assert loss.is_cuda and all(g.is_cuda and g.shape == (prob.nz, prob.nx) for g in grads)
+        vals[compat] = (loss.item(), max(float(g.abs().max()) for g in grads))
+    print("experiment %s: f(x0) = %.6e (log %.5e); |proj g| = %.5f race-compat, %.5f race-free (log %.5f)"
+          % (kind, vals[True][0], f0, vals[True][1], vals[False][1], g0))
+    assert abs(vals[True][0] - f0) <= 2e-5 * f0 and vals[False][0] == vals[True][0]
+    assert min(abs(vals[True][1] - g0), abs(vals[False][1] - g0)) <= 0.03 * g0
+    fwi_ops.clear_cache()
+
+
+def test_every_parameterisation_module_on_cuda_tensors(tmp_path):
+    """FWI, FWI_Lame_Den, FWI_IP_IS_Den, FWI_Vp_Vs_IP, FWI_Vp_Vs_IS, FWI_Rock_Physics_VRH / _gassmann through the op on the
+    GPU: equivalent parameters give the same misfit, and every module's gradient is the chain rule of its to_lame map applied
+    to the (lambda, mu, rho) gradient the op returns (vector-Jacobian product by autograd, checked against the module)."""
+    import torch
+    from sepfwi import FWI_ops as F, fwi_ops, fwi_utils as ft
+    prob = problems.tiny()
+    work = str(tmp_path)
+    para, survey, data = work + "/para.json", work + "/survey.json", work + "/d"
+    ft.paraGen(prob.nz, prob.nx, prob.dz, prob.dx, prob.nSteps, prob.dt, prob.f0, prob.nPml, prob.nPad, para, survey, data)
+    ft.surveyGen(prob.z_src, prob.x_src, prob.z_rec, prob.x_rec, survey)
+    dev = "cuda"
+    T = lambda a: torch.tensor(np.ascontiguousarray(a, np.float32), device=dev)
+    stf, ids = T(prob.stf), torch.arange(prob.nshots, dtype=torch.int32, device=dev)
+    fwi_ops.obscalc(*map(T, prob.true), stf, 1, ids, para)
+    nzo, nxo, P0 = prob.nz_orig, prob.nx_orig, prob.nPml
+    crop = lambda a: np.ascontiguousarray(a[P0:P0 + nzo, P0:P0 + nxo])
+    lam, mu, den = (crop(a).astype(np.float64) for a in prob.start)
+    vp, vs = np.sqrt((lam + 2 * mu) * 1e6 / den), np.sqrt(mu * 1e6 / den)
+    opt = dict(nz=nzo, nx=nxo, nz_orig=nzo, nx_orig=nxo, nPml=P0, nPad=prob.nPad, para_fname=para)
+    cases = {"FWI": (F.FWI, (vp, vs, den)), "FWI_Lame_Den": (F.FWI_Lame_Den, (lam, mu, den)),
+             "FWI_IP_IS_Den": (F.FWI_IP_IS_Den, (vp * den / 1e3, vs * den / 1e3, den)),
+             "FWI_Vp_Vs_IP": (F.FWI_Vp_Vs_IP, (vp, vs, vp * den)), "FWI_Vp_Vs_IS": (F.FWI_Vp_Vs_IS, (vp, vs, vs * den))}
+    losses, base = {}, None
+    for name, (cls, fields) in cases.items():
+        th = [torch.tensor(a, dtype=torch.float32, device=dev, requires_grad=True) for a in fields]
+        m = cls(*th, stf, opt)
+        loss = m(ids, ngpu=1)
+        loss.backward()
+        losses[name] = loss.item()
+        grads = [getattr(m, n).grad for n in m.NAMES]
+        assert all(g is not None and g.is_cuda and float(g.abs().max()) > 0 for g in grads), name
+        # chain rule: the op's (lambda, mu, rho) gradient pulled back through to_lame by autograd
+        with torch.no_grad():
+            out = fwi_ops.backward(*cls.to_lame(*m._masked()), stf, 1, ids, para)
+        x = [t.detach().clone().requires_grad_(True) for t in th]
+        pads = ft.padding(*x, nzo, nxo, nzo, nxo, P0, prob.nPad)
+        L = cls.to_lame(*pads)
+        torch.autograd.backward(L, [g.to(dev) for g in out[1:4]])
+        for a, b in zip(grads, x):
+            assert rel_l2(a.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5, name
+    for name, v in losses.items():
+        if name.startswith("FWI_Vp_Vs_I"):
+            continue      # lambda, mu in Pa there (FWI_ops.py:324-328, 390-392, reproduced): a different (much stiffer) medium
+        assert abs(v - losses["FWI"]) <= 2e-4 * abs(losses["FWI"]), (name, v, losses["FWI"])
+    # rock physics: porosity / clay / saturation fields whose velocities respect the CFL limit of this grid
+    rng = np.random.default_rng(4)
+    phi = 0.25 + 0.05 * problems.smooth(rng.uniform(-1, 1, (nzo, nxo)), 4)
+    cc = 0.3 + 0.1 * problems.smooth(rng.uniform(-1, 1, (nzo, nxo)), 4)
+    sw = 0.6 + 0.2 * problems.smooth(rng.uniform(-1, 1, (nzo, nxo)), 4)
+    for cls in (F.FWI_Rock_Physics_VRH, F.FWI_Rock_Physics_gassmann):
+        th = [torch.tensor(a, dtype=torch.float32, device=dev, requires_grad=True) for a in (phi, cc, sw)]
+        m = cls(*th, stf, opt)
+        loss = m(ids, ngpu=1)
+        loss.backward()
+        assert loss.is_cuda and np.isfinite(loss.item()) and loss.item() > 0
+        for n in m.NAMES:
+            g = getattr(m, n).grad
+            assert g is not None and g.is_cuda and torch.isfinite(g).all() and float(g.abs().max()) > 0, (cls.__name__, n)
+    fwi_ops.clear_cache()

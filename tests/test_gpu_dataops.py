@@ -1,0 +1,147 @@
+"""GPU tests (-m gpu) of the data-side operators (trace windows + weights, band-pass, normalised
+cross-correlation misfit, source-signature update; Src/utilities.cu:733-1356, call sites libCUFD.cu:353-457) against the
+numpy restatement oracle/dataops.py, and of their wiring into the gradient and the reference-facing op."""
+import os
+
+import numpy as np
+import pytest
+
+import problems
+from util import cuda_shots, make_prop, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_traces(nrec, nt, dt, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(nt) * dt
+    out = np.zeros((nrec, nt))
+    for r in range(nrec):
+        for f in rng.uniform(4.0, 60.0, 5):
+            out[r] += rng.normal() * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
+        out[r] *= np.exp(-((t - 0.45 * nt * dt) / (0.2 * nt * dt)) ** 2) * 1e2
+    return out.astype(np.float32)
+
+
+def _windows(nrec, nt, dt):
+    return (np.linspace(0.05, 0.2, nrec) * nt * dt).astype(np.float32), (np.linspace(0.7, 0.95, nrec) * nt * dt).astype(np.float32), \
+        np.linspace(0.5, 1.5, nrec).astype(np.float32)
+
+
+OPTS = [dict(filter=[8.0, 15.0, 30.0, 45.0]), dict(if_win=True), dict(if_cross_misfit=True), dict(if_src_update=True),
+        dict(if_win=True, filter=[8.0, 15.0, 30.0, 45.0]), dict(if_win=True, if_cross_misfit=True, filter=[8.0, 15.0, 30.0, 45.0]),
+        dict(if_src_update=True, filter=[8.0, 15.0, 30.0, 45.0], if_win=True)]
+
+
+@pytest.mark.parametrize("opts", OPTS)
+@pytest.mark.parametrize("mk", [problems.tiny, problems.small])
+def test_condition_matches_oracle(mk, opts):
+    """sepfwi_condition (the chain alone, no propagation) on random traces: adjoint source, conditioned synthetic, misfit and
+    updated source against oracle/dataops.condition.  fp32 direct transforms vs float64 FFTs: 1e-4."""
+    from oracle import dataops as D
+    from sepfwi.engine import Propagator, ShotSpec
+    prob = mk()
+    nrec, nt, dt = len(prob.x_rec), prob.nSteps, prob.dt
+    obs, cal = _random_traces(nrec, nt, dt, 1), _random_traces(nrec, nt, dt, 2)
+    cal = (0.6 * obs + 0.4 * cal).astype(np.float32)
+    ws, we, wt = _windows(nrec, nt, dt)
+    with make_prop(Propagator, prob, max_batch=1, with_adjoint=True) as P:
+        sh = cuda_shots(prob, ShotSpec, [0])[0]
+        kw = {}
+        if opts.get("if_win"):
+            sh.win_start, sh.win_end, sh.trace_weights, sh.src_weight = ws, we, wt, 0.75
+            kw = dict(win_start=ws, win_end=we, weights=wt, src_weight=0.75)
+        P.set_data_options(**opts)
+        got = P.condition(sh, obs, cal)
+    o = dict(opts)
+    filt = o.pop("filter", None)
+    # the source the chain sees: tapered (Src_Rec.cu:137) stf
+    from oracle import oracle as O
+    src = O.stf_taper(prob.stf[0], dt)
+    ref = D.condition(obs, cal, src, dt, filt=filt, **o, **kw)
+    assert rel_l2(got["res"], ref["res"]) < 1e-4, rel_l2(got["res"], ref["res"])
+    assert rel_l2(got["syn"], ref["cal"]) < 1e-4
+    assert abs(got["misfit"] - 0.5 * ref["misfit"]) <= 1e-4 * abs(0.5 * ref["misfit"])
+    if opts.get("if_src_update"):
+        assert rel_l2(got["src_updated"], ref["src"]) < 1e-3, rel_l2(got["src_updated"], ref["src"])
+
+
+@pytest.mark.parametrize("opts", [dict(if_win=True, filter=[6.0, 10.0, 25.0, 40.0]), dict(if_cross_misfit=True)])
+def test_gradient_with_data_options_uses_the_conditioned_adjoint_source(opts):
+    """Wiring into sepfwi_gradient: with options on, misfit = the chain's misfit and the gradient = the plain-L2 gradient for
+    observed data chosen so that the plain residual equals the conditioned adjoint source (the adjoint and the imaging are
+    linear in the adjoint source)."""
+    from sepfwi.engine import Propagator, ShotSpec
+    prob = problems.small()
+    nrec, nt, dt = len(prob.x_rec), prob.nSteps, prob.dt
+    ws, we, wt = _windows(nrec, nt, dt)
+    with make_prop(Propagator, prob, max_batch=3, with_adjoint=True) as P:
+        shots = cuda_shots(prob, ShotSpec)
+        for sh in shots:
+            sh.win_start, sh.win_end, sh.trace_weights, sh.src_weight = ws, we, wt, 1.25
+        P.set_model(*prob.true)
+        obs = [f["ett"] for f in P.forward(shots, comps=("ett",))]
+        P.set_model(*prob.start)
+        P.set_data_options(**opts)
+        r = P.gradient(shots, obs, want_syn=True)
+        cond = [P.condition(sh, o, s) for sh, o, s in zip(shots, obs, r["syn"])]
+        assert abs(sum(c["misfit"] for c in cond) - r["misfit64"]) <= 1e-6 * abs(r["misfit64"])
+        P.set_data_options()                                                   # all off: plain residual obs' - syn
+        fake = [(s + c["res"]).astype(np.float32) for s, c in zip(r["syn"], cond)]
+        p = P.gradient(shots, fake)
+    for k in ("glam", "gmu", "grho"):
+        assert np.abs(p[k]).max() > 0 and rel_l2(r[k], p[k]) < 2e-4, (k, rel_l2(r[k], p[k]))
+    assert rel_l2(np.stack(r["gstf"]), np.stack(p["gstf"])) < 2e-4
+
+
+def test_data_options_through_para_file_python_op_and_c_dropin(tmp_path):
+    """`filter` + `if_win` in para_file.json / survey_file.json: the reference-facing Python op and the C drop-in
+    (sepfwi_cufd) give the engine's result; switching the options off again restores the plain misfit."""
+    import torch
+    from sepfwi import _lib, fwi_ops, fwi_utils as ft
+    from sepfwi.engine import Propagator, ShotSpec
+    prob = problems.tiny()
+    nrec, nt, dt = len(prob.x_rec), prob.nSteps, prob.dt
+    ws, we, wt = _windows(nrec, nt, dt)
+    filt = [10.0, 18.0, 40.0, 60.0]
+    ids = np.arange(prob.nshots, dtype=np.int32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32))
+    out = {}
+    for tag, on in (("on", True), ("off", False)):
+        work = str(tmp_path / tag)
+        os.makedirs(work)
+        para, survey, data = work + "/para.json", work + "/survey.json", work + "/d"
+        ft.paraGen(prob.nz, prob.nx, prob.dz, prob.dx, nt, dt, prob.f0, prob.nPml, prob.nPad, para, survey, data,
+                   if_win=on, filter_para=filt if on else None)
+        W = {"shot%d" % i: {"start": ws.tolist(), "end": we.tolist()} for i in ids}
+        Wt = {"shot%d" % i: {"weights": wt.tolist()} for i in ids}
+        ft.surveyGen(prob.z_src, prob.x_src, prob.z_rec, prob.x_rec, survey, Windows=W if on else None, Weights=Wt if on else None,
+                     Src_Weights=[1.25] * len(ids) if on else None)
+        fwi_ops.obscalc(*map(T, prob.true), T(prob.stf), 1, torch.from_numpy(ids), para)
+        py = fwi_ops.backward(*map(T, prob.start), T(prob.stf), 1, torch.from_numpy(ids), para)
+        lam, mu, den = (np.ascontiguousarray(a, np.float32) for a in prob.start)
+        stf = np.ascontiguousarray(prob.stf, np.float32)
+        J = np.zeros(1, np.float32)
+        g = [np.zeros_like(lam) for _ in range(3)]
+        gs = np.zeros_like(stf)
+        p = lambda a: a.ctypes.data
+        _lib.check(_lib.lib().sepfwi_cufd(p(J), p(g[0]), p(g[1]), p(g[2]), p(gs), p(lam), p(mu), p(den), p(stf), 1, 0, ids.size, p(ids), para.encode()))
+        out[tag] = (py[0].item(), py[1].numpy(), float(J[0]), g[0])
+        assert abs(out[tag][0] - out[tag][2]) <= 1e-6 * abs(out[tag][0])
+        assert rel_l2(out[tag][3], out[tag][1]) < 1e-6
+    # engine directly
+    with make_prop(Propagator, prob, max_batch=2, with_adjoint=True) as P:
+        shots = cuda_shots(prob, ShotSpec)
+        P.set_model(*prob.true)
+        obs = [f["ett"] for f in P.forward(shots, comps=("ett",))]
+        P.set_model(*prob.start)
+        plain = P.gradient(shots, obs)
+        for sh in shots:
+            sh.win_start, sh.win_end, sh.trace_weights, sh.src_weight = ws, we, wt, 1.25
+        P.set_data_options(if_win=True, filter=filt)
+        cond = P.gradient(shots, obs)
+    assert abs(out["on"][0] - cond["misfit"]) <= 1e-6 * abs(cond["misfit"]) and rel_l2(out["on"][1], cond["glam"]) < 1e-6
+    assert abs(out["off"][0] - plain["misfit"]) <= 1e-6 * abs(plain["misfit"]) and rel_l2(out["off"][1], plain["glam"]) < 1e-6
+    assert abs(cond["misfit"] - plain["misfit"]) > 0.05 * abs(plain["misfit"])
+    _lib.lib().sepfwi_cufd_clear_cache()
+    fwi_ops.clear_cache()

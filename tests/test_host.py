@@ -38,14 +38,14 @@ def test_struct_layouts_match_header():
     """ctypes mirrors of sepfwi_params / sepfwi_shot have the C sizes (checked against a compiled probe)."""
     import ctypes as C
     from sepfwi import _lib
-    src = '#include <stdio.h>\n#include "sepfwi.h"\nint main(){printf("%zu %zu\\n", sizeof(sepfwi_params), sizeof(sepfwi_shot));return 0;}\n'
+    src = '#include <stdio.h>\n#include "sepfwi.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(sepfwi_params), sizeof(sepfwi_shot), sizeof(sepfwi_data_options));return 0;}\n'
     exe = os.path.join(ROOT, "tests", "_probe_sizes")
     p = subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src, text=True,
                        capture_output=True)
     assert p.returncode == 0, p.stderr
-    a, b = map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split())
+    a, b, c = map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split())
     os.unlink(exe)
-    assert C.sizeof(_lib.Params) == a and C.sizeof(_lib.Shot) == b
+    assert C.sizeof(_lib.Params) == a and C.sizeof(_lib.Shot) == b and C.sizeof(_lib.DataOptions) == c
 
 
 def test_no_gpu_means_loud_failure():
