@@ -1179,4 +1179,209 @@ __global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, 
     else stream_rec_body<true>(a, sa, s, wk, lane, sw, sp);
 }
 
+// ================================================================================================
+// Sponge flavour (DAS_Waveform_Modeling/src/elasticSolver.py:241-276, the Numba CPU propagator's scheme) as ONE launch per time step:
+//   phase A (row r)    v  = damp (v + D(sigma) b dt)            update_velocity :310-345 + the sponge :247-248
+//   phase B (row r-2)  sigma = damp (sigma + C D(v_new) dt) + stf dt / 2 at the source   update_stress :348-386, :253-260
+// the order (velocity first, stresses from the NEW velocities) is the adjoint sweep's march; no CPML memory, the multiplicative
+// sponge is one more operand row.  The 2-cell rim never moves (update_* loop over [2, n-2)), so every warp runs the same body
+// with an active-cell select.  Traces of sample it-1 (recorded AFTER step it-1, :263-276: pressure halved, strain rates divided by
+// the spacing) are written by the leading CTAs from the old state; the host records the last sample after the loop.
+constexpr int SP_NARR = 12, SP_NST = 3;
+constexpr int SP_WARP_BYTES = SP_NARR * SP_NST * 512;          // 18 KB per warp
+constexpr size_t SP_SMEM = (size_t)SW_WPB * SP_WARP_BYTES;     // 72 KB per CTA
+enum { SA_SZ = 0, SA_SX, SA_SXZ, SA_OVZ, SA_OVX, SA_BYA, SA_BYB, SA_DV,      // rows r+2 (stresses), r
+       SA_LAM, SA_MU, SA_MUA, SA_DS };                                        // row r-2
+
+struct SpCtx {
+    const float *g, *m, *damp, *amp;
+    float *o;
+    const float4 *ring_p;
+    unsigned ring_s;
+    size_t fsz;
+    int ld, nzA, zc0, zc1, zs, xs, xq0;
+    unsigned amask;
+    bool lown;
+    float c1z, c2z, c1x, c2x, dt;
+};
+struct SpWin { float4 sz[6], sx[6], sxz[6], vz[6], vx[6]; };
+
+__device__ __forceinline__ void stream_sp_issue(const SpCtx &k, const int r, const int stage)
+{
+    const int ld = k.ld, nzA = k.nzA;
+    const size_t fsz = k.fsz;
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };
+    const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
+    const unsigned sb = k.ring_s + (unsigned)stage * (SP_NARR * 512);
+    cp16(sb + SA_SZ * 512, k.g + F_SZZ * fsz + r2); cp16(sb + SA_SX * 512, k.g + F_SXX * fsz + r2); cp16(sb + SA_SXZ * 512, k.g + F_SXZ * fsz + r2);
+    cp16(sb + SA_OVZ * 512, k.g + F_VZ * fsz + r0); cp16(sb + SA_OVX * 512, k.g + F_VX * fsz + r0);
+    cp16(sb + SA_BYA * 512, k.m + M_BYCA * fsz + r0); cp16(sb + SA_BYB * 512, k.m + M_BYCB * fsz + r0); cp16(sb + SA_DV * 512, k.damp + r0);
+    cp16(sb + SA_LAM * 512, k.m + M_LAM * fsz + rq); cp16(sb + SA_MU * 512, k.m + M_MU * fsz + rq); cp16(sb + SA_MUA * 512, k.m + M_MUAVE * fsz + rq);
+    cp16(sb + SA_DS * 512, k.damp + rq);
+    cp_commit();
+}
+
+template <int U>
+__device__ __forceinline__ void stream_sp_row(const SpCtx &k, SpWin &w, const int r, const int stage)
+{
+    const int ld = k.ld, nzA = k.nzA;
+    const size_t fsz = k.fsz;
+    const float c1z = k.c1z, c2z = k.c2z, c1x = k.c1x, c2x = k.c2x, dt = k.dt;
+    constexpr int u = U;
+    stream_sp_issue(k, r + (SP_NST - 1), stage == 0 ? SP_NST - 1 : stage - 1);
+    cp_wait<SP_NST - 1>();
+    const float4 *sb = k.ring_p + stage * (SP_NARR * 32);
+    w.sz[(u + 4) % 6] = sb[SA_SZ * 32]; w.sx[(u + 4) % 6] = sb[SA_SX * 32]; w.sxz[(u + 4) % 6] = sb[SA_SXZ * 32];     // row r+2
+    // ---- phase A: velocities at row r from the old stresses, rows r-2 .. r+2 (slots u .. u+4)
+    {
+        const float4 z1 = w.sz[(u + 2) % 6], z2 = w.sz[(u + 3) % 6], z3 = w.sz[(u + 4) % 6], z0 = w.sz[(u + 1) % 6];
+        const float4 q0 = w.sxz[u % 6], q1 = w.sxz[(u + 1) % 6], q2 = w.sxz[(u + 2) % 6], q3 = w.sxz[(u + 3) % 6];
+        const float4 xc = w.sx[(u + 2) % 6];
+        const float wxz[7] = XWIN_B(q2), wxx[7] = XWIN_F(xc);
+        const float zzm1[4] = Q4(z0), zzc[4] = Q4(z1), zzp1[4] = Q4(z2), zzp2[4] = Q4(z3);
+        const float xzm2[4] = Q4(q0), xzm1[4] = Q4(q1), xzc[4] = Q4(q2), xzp1[4] = Q4(q3);
+        const float4 ovz4 = sb[SA_OVZ * 32], ovx4 = sb[SA_OVX * 32], ba4 = sb[SA_BYA * 32], bb4 = sb[SA_BYB * 32], dv4 = sb[SA_DV * 32];
+        const float ovz[4] = Q4(ovz4), ovx[4] = Q4(ovx4), ba[4] = Q4(ba4), bb[4] = Q4(bb4), dv[4] = Q4(dv4);
+        float nvz[4], nvx[4];
+        const bool rowact = (r >= 2 && r <= nzA - 3);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            // dszz/dz forward, dsxz/dx backward -> vz ; dsxz/dz backward, dsxx/dx forward -> vx   (k_velocity_fwd<true>)
+            const float dszz_dz = DZ4(zzm1[c], zzc[c], zzp1[c], zzp2[c]);
+            const float dsxz_dx = DX7(wxz, c);
+            const float dsxz_dz = DZ4(xzm2[c], xzm1[c], xzc[c], xzp1[c]);
+            const float dsxx_dx = DX7(wxx, c);
+            const bool act = rowact && ((k.amask >> c) & 1u);
+            const float tvz = (ovz[c] + (dszz_dz + dsxz_dx) * ba[c] * dt) * dv[c];
+            const float tvx = (ovx[c] + (dsxz_dz + dsxx_dx) * bb[c] * dt) * dv[c];
+            nvz[c] = act ? tvz : ovz[c]; nvx[c] = act ? tvx : ovx[c];
+        }
+        const float4 rvz = mk4(nvz), rvx = mk4(nvx);
+        w.vz[(u + 4) % 6] = rvz; w.vx[(u + 4) % 6] = rvx;              // new velocity row r-j lives in slot u+4-j
+        const bool rown = (r >= k.zc0) && (r < k.zc1);
+        if (k.lown && rown) { const size_t ro = (size_t)r * ld; stq(k.o + F_VZ * fsz + ro, rvz); stq(k.o + F_VX * fsz + ro, rvx); }
+    }
+    // ---- phase B: stresses at row q = r-2 from the new velocities: vz rows q-2..q+1, vx rows q-1..q+2
+    {
+        const int q = r - 2;
+        const float4 v0 = w.vz[u % 6], v1 = w.vz[(u + 1) % 6], v2 = w.vz[(u + 2) % 6], v3 = w.vz[(u + 3) % 6];
+        const float4 u0 = w.vx[(u + 1) % 6], u1 = w.vx[(u + 2) % 6], u2 = w.vx[(u + 3) % 6], u3 = w.vx[(u + 4) % 6];
+        const float wvz[7] = XWIN_F(v2), wvx[7] = XWIN_B(u1);
+        const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
+        const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
+        const float ozz[4] = Q4(w.sz[u % 6]), oxx[4] = Q4(w.sx[u % 6]), oxz[4] = Q4(w.sxz[u % 6]);     // old stresses of row r-2: slot u
+        const float4 lam4 = sb[SA_LAM * 32], mu4 = sb[SA_MU * 32], mua4 = sb[SA_MUA * 32], ds4 = sb[SA_DS * 32];
+        const float l[4] = Q4(lam4), mm[4] = Q4(mu4), ma[4] = Q4(mua4), ds[4] = Q4(ds4);
+        float nzz[4], nxz[4], nxx[4];
+        const bool qown = (q >= k.zc0) && (q < k.zc1);
+        const bool rowact = (q >= 2 && q <= nzA - 3);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            // dvz/dz backward, dvx/dx backward -> szz, sxx ; dvx/dz forward, dvz/dx forward -> sxz   (k_stress_fwd<true>)
+            const float dvz_dz = DZ4(vzm2[c], vzm1[c], vzc[c], vzp1[c]);
+            const float dvx_dx = DX7(wvx, c);
+            const float dvx_dz = DZ4(vxm1[c], vxc[c], vxp1[c], vxp2[c]);
+            const float dvz_dx = DX7(wvz, c);
+            const bool act = rowact && ((k.amask >> c) & 1u);
+            const float l2u = l[c] + 2.0f * mm[c];
+            float tzz = (ozz[c] + (l2u * dvz_dz + l[c] * dvx_dx) * dt) * ds[c];
+            float txx = (oxx[c] + (l[c] * dvz_dz + l2u * dvx_dx) * dt) * ds[c];
+            const float txz = (oxz[c] + ma[c] * (dvx_dz + dvz_dx) * dt) * ds[c];
+            if (q == k.zs && k.xq0 + c == k.xs) { const float amp = *k.amp; tzz += amp; txx += amp; }      // after the sponge, :259-260
+            nzz[c] = act ? tzz : ozz[c]; nxx[c] = act ? txx : oxx[c]; nxz[c] = act ? txz : oxz[c];
+        }
+        if (k.lown && qown) {
+            const size_t ro = (size_t)q * ld;
+            stq(k.o + F_SZZ * fsz + ro, mk4(nzz)); stq(k.o + F_SXZ * fsz + ro, mk4(nxz)); stq(k.o + F_SXX * fsz + ro, mk4(nxx));
+        }
+    }
+}
+
+// traces of sample `samp` from the state in buffer `par` (k_record<true> arithmetic)
+__device__ __forceinline__ void stream_sp_aux(const KArgs &a, const StreamArgs &sa, int s, int samp, int par)
+{
+    const Dims &d = a.d;
+    const int ld = d.ldx;
+    const float *src = slot_state(a, s) + (size_t)(par ? S_FWD1 : S_FWD) * d.fsz;
+    const int nth = sa.nAux * SW_NT, t0 = blockIdx.x * SW_NT + threadIdx.x;
+    const int nrec = a.t.nrec[s];
+    const size_t cs = (size_t)d.maxRec * d.nSteps;
+    const float *vz = src + (size_t)F_VZ * d.fsz, *vx = src + (size_t)F_VX * d.fsz;
+    for (int r = t0; r < nrec; r += nth) {
+        const int z = a.t.zrec[(size_t)s * d.maxRec + r], x = a.t.xrec[(size_t)s * d.maxRec + r];
+        const size_t i = (size_t)z * ld + x;
+        float *tr = a.trace + (size_t)s * d.nTrace * cs + (size_t)r * d.nSteps + samp;
+        const float exx = (vx[i] - vx[i - 1]) * d.rdx, ezz = (vz[i] - vz[i - ld]) * d.rdz;
+        const float exz = 0.5f * ((vx[i + ld] - vx[i]) * d.rdz + (vz[i + 1] - vz[i]) * d.rdx);
+        if (sa.mask & (1 << T_PR)) tr[T_PR * cs] = 0.5f * (src[(size_t)F_SXX * d.fsz + i] + src[(size_t)F_SZZ * d.fsz + i]);
+        if (sa.mask & (1 << T_VX)) tr[T_VX * cs] = vx[i];
+        if (sa.mask & (1 << T_VZ)) tr[T_VZ * cs] = vz[i];
+        if (sa.mask & (1 << T_ETT)) {
+            const float *w = a.t.w ? a.t.w + ((size_t)s * d.maxRec + r) * 3 : nullptr;
+            tr[T_ETT * cs] = w ? w[0] * exx + w[1] * ezz + w[2] * exz : (sa.fiber == 0 ? exx : ezz);
+        }
+        if (sa.mask & (1 << T_EXX)) tr[T_EXX * cs] = exx;
+        if (sa.mask & (1 << T_EZZ)) tr[T_EZZ * cs] = ezz;
+        if (sa.mask & (1 << T_EXZ)) tr[T_EXZ * cs] = exz;
+    }
+}
+
+// grid: x = nAux + ceil(nWork / SW_WPB), y = slot ; dynamic shared memory SP_SMEM ; time step sa.it reads buffer it & 1
+__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_sponge(const KArgs a, const StreamArgs sa)
+{
+    extern __shared__ __align__(16) float smem[];
+    pdl_launch_dependents();
+    const int s = blockIdx.y;
+    const int p = sa.it & 1;
+    if ((int)blockIdx.x < sa.nAux) { pdl_wait(); if (sa.mask) stream_sp_aux(a, sa, s, sa.it - 1, p); return; }
+    const int wg = ((int)blockIdx.x - sa.nAux) * SW_WPB + ((int)threadIdx.x >> 5);
+    if (wg >= sa.nWork) return;
+    const int4 wk = __ldg(sa.work + wg);
+    const int lane = threadIdx.x & 31;
+    const Dims &d = a.d;
+    SpCtx k;
+    k.ld = d.ldx; k.nzA = d.nzA; k.fsz = d.fsz;
+    const size_t fsz = d.fsz;
+    float *st = slot_state(a, s);
+    k.xq0 = wk.x - 4 + 4 * lane;
+    const bool colok = (k.xq0 >= 0) && (k.xq0 < d.ldx);
+    const int xq = colok ? k.xq0 : 0;
+    k.g = st + (size_t)(p ? S_FWD1 : S_FWD) * fsz + xq;
+    k.o = st + (size_t)(p ? S_FWD : S_FWD1) * fsz + xq;
+    k.m = a.model + xq; k.damp = a.damp + xq;
+    k.amp = a.t.amp + (size_t)s * d.nSteps + sa.it;
+    k.zc0 = wk.y; k.zc1 = wk.z;
+    k.lown = (lane >= 1) && (lane <= 30) && colok;
+    k.zs = a.t.zs[s]; k.xs = a.t.xs[s];
+    k.c1z = d.c1z; k.c2z = d.c2z; k.c1x = d.c1x; k.c2x = d.c2x; k.dt = d.dt;
+    k.ring_s = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * SP_WARP_BYTES + lane * 16;
+    k.ring_p = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (SP_WARP_BYTES / 16) + lane;
+    k.amask = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) { const int x = k.xq0 + c; if (x >= 2 && x <= d.nx - 3) k.amask |= 1u << c; }
+    SpWin w;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 6; j++) { w.sz[j] = w.sx[j] = w.sxz[j] = w.vz[j] = w.vx[j] = zero; }
+    auto rowoff = [&](int row) { return (size_t)min(max(row, 0), d.nzA - 1) * d.ldx; };
+    const int r0 = k.zc0 - 2;
+    pdl_wait();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {       // old stress rows r0-2 .. r0+1 ; row r+2 arrives through the ring
+        const size_t ro = rowoff(r0 - 2 + j);
+        w.sz[j] = ldq(k.g + F_SZZ * fsz + ro); w.sx[j] = ldq(k.g + F_SXX * fsz + ro); w.sxz[j] = ldq(k.g + F_SXZ * fsz + ro);
+    }
+#pragma unroll
+    for (int j = 0; j < SP_NST - 1; j++) stream_sp_issue(k, r0 + j, j);
+    const int niter = (k.zc1 - k.zc0) + 4;
+    int stg = 0;
+#pragma unroll 1
+    for (int kk = 0; kk < niter; kk += 2) {
+        stream_sp_row<0>(k, w, r0 + kk, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
+        stream_sp_row<1>(k, w, r0 + kk + 1, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
+        win_shift<2>(w.sz); win_shift<2>(w.sx); win_shift<2>(w.sxz); win_shift<2>(w.vz); win_shift<2>(w.vx);
+    }
+    cp_wait<0>();
+}
+
 }  // namespace sepfwi

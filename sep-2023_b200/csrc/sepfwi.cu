@@ -64,6 +64,7 @@ struct sepfwi_handle {
     size_t o_zs, o_xs, o_nrec, o_zrec, o_xrec, o_injN, o_injCell, o_injField, o_injPtr, o_injRec, o_sInjPtr, o_sInj;
     int nStrips = 0;
     bool stream = false;   // register-streaming kernels (kernels = 0 / 3); otherwise the unfused baseline kernels
+    bool stream_sponge = false;   // sponge flavour through k_stream_sponge (kernels = 0 / 3)
     int nSM = 148;
     size_t smem_optin = 0; // largest opt-in dynamic shared memory per block on this device
     bool pdl = true;       // programmatic dependent launch inside the time loops (SEPFWI_PDL=0 disables)
@@ -400,6 +401,8 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         h->nSM = prop.multiProcessorCount;
         h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     }
+    h->stream_sponge = h->sponge && pp->kernels != 1;
+    if (h->stream_sponge) CU(cudaFuncSetAttribute(k_stream_sponge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM + h->smem_pad));
     if (h->stream) {
         CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM + h->smem_pad));
         CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM + h->smem_pad));
@@ -1108,6 +1111,34 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
             LAUNCH(h, SEPFWI_K_VELOCITY_FWD, pr, st, (k_velocity_fwd<false><<<grd, blk, 0, st>>>(a)));
             if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, pr, st, (k_record<false><<<rgrd, 128, 0, st>>>(a, it + 1, mask, h->p.fiber, 0)));
         }
+    } else if (h->stream_sponge) {
+        // sponge flavour, one launch per time step (elasticSolver.py:241-276): step `it` reads buffer it & 1; the traces of sample
+        // it - 1 are written by the launch of step it from its input state, the last sample after the loop
+        StreamArgs sa;
+        int rc = stream_plan(h, nb, 0, sa, st);
+        if (rc) return rc;
+        sa.fiber = h->p.fiber; sa.nrecMax = mrec;
+        sa.nAux = mrec > 0 ? std::min(h->nSM, (mrec + 2 * SW_NT - 1) / (2 * SW_NT)) : 0;
+        dim3 sgrd(sa.nAux + (sa.nWork + SW_WPB - 1) / SW_WPB, nb);
+        const int nzI = d.nzA - 2 * d.nPml, nxI = d.nx - 2 * d.nPml;
+        for (int it = 0; it < d.nSteps; it++) {
+            const bool pr = it < h->prof_steps;
+            sa.it = it; sa.mask = (it >= 1 && mrec > 0) ? mask : 0;
+            cudaError_t le = cudaSuccess;
+            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (le = launch_pdl(k_stream_sponge, sgrd, dim3(SW_NT), SP_SMEM + h->smem_pad, st, h->pdl, a, sa)));
+            CU(le);
+            if (h->snap_dst && it % h->snap_step == 0) {
+                static const int fld[4] = {F_SXX, F_SZZ, F_VX, F_VZ};
+                const int buf = ((it + 1) & 1) ? S_FWD1 : S_FWD;          // where the state after step `it` lives
+                float *dst = h->snap_dst + (size_t)(it / h->snap_step) * 4 * nzI * nxI;
+                for (int f = 0; f < 4; f++)
+                    CU(cudaMemcpy2DAsync(dst + (size_t)f * nzI * nxI, (size_t)nxI * sizeof(float),
+                                         h->state + (size_t)(buf + fld[f]) * d.fsz + (size_t)d.nPml * d.ldx + d.nPml, (size_t)d.ldx * sizeof(float),
+                                         (size_t)nxI * sizeof(float), nzI,
+                                         h->snap_mem == SEPFWI_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        if (mrec > 0) LAUNCH(h, SEPFWI_K_RECORD, false, st, (k_record<true><<<rgrd, 128, 0, st>>>(a, d.nSteps - 1, mask, h->p.fiber, d.nSteps & 1)));
     } else {
         const int nzI = d.nzA - 2 * d.nPml, nxI = d.nx - 2 * d.nPml;
         for (int it = 0; it < d.nSteps; it++) {

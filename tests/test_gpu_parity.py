@@ -549,3 +549,37 @@ def test_cufd_dropin_reads_das_sensitivity(tmp_path):
         assert rel_l2(a, b) < 1e-6
     _lib.lib().sepfwi_cufd_clear_cache()
     fwi_ops.clear_cache()
+
+
+@pytest.mark.parametrize("nx,nb", [(291, 2), (250, 1), (97, 3)])
+def test_sponge_flavour_streaming_kernel_matches_unfused_kernels(nx, nb):
+    """Sponge flavour (the Numba propagator's scheme: velocity -> sponge -> stress -> sponge -> source -> record) through
+    k_stream_sponge (one launch per step, kernels = 0) against the three unfused launches per step (kernels = 1): all seven
+    trace components, several strips with odd widths, receivers on strip seams and next to the rim, several shots per launch."""
+    from sepfwi import _lib
+    _, Propagator, ShotSpec = _mods()
+    rng = np.random.default_rng(nx)
+    nz, nd, nt = 120, 20, 220
+    vp = problems.layered_vp(nz, nx, 1800.0, 3400.0, 5, rng, nlens=8, lens_amp=0.1, sigma=(4, 14))
+    vpp = np.pad(vp, nd, mode="edge")
+    lam, mu, rho = problems.lame_from_vp(vpp)
+    model = [np.ascontiguousarray(lam * 1e6, np.float32), np.ascontiguousarray(mu * 1e6, np.float32), rho]
+    NZ, NX = vpp.shape
+    stf = problems.ricker(20.0, nt, 1e-3, amp=1.0)
+    shots = []
+    for k in range(nb):
+        nrec = 60
+        zr = rng.integers(1, NZ - 2, nrec)
+        xr = np.concatenate([rng.integers(1, NX - 2, nrec - 8), [1, NX - 2, 119, 120, 121, 124, min(240, NX - 2), min(239, NX - 2)]])
+        w = rng.uniform(-1, 1, (nrec, 3)).astype(np.float32) if k == 0 else None
+        shots.append(ShotSpec(nd + 5 + 10 * k, nd + nx // 2 + 7 * k, zr, xr, stf, weights=w))
+    res = {}
+    for kern in (0, 1):
+        with Propagator(NZ, NX, nd, 0, nt, 10.0, 10.0, 1e-3, 20.0, flavour=_lib.FLAVOUR_SPONGE, max_batch=nb, max_nrec=60, device=0,
+                        kernels=kern) as P:
+            P.set_model(*model)
+            res[kern] = P.forward(shots, comps=("pr", "vx", "vz", "ett", "exx", "ezz", "exz"))
+    for k in range(nb):
+        for c in ("pr", "vx", "vz", "ett", "exx", "ezz", "exz"):
+            assert np.abs(res[1][k][c]).max() > 0
+            assert rel_l2(res[0][k][c], res[1][k][c]) < 1e-5, (k, c, rel_l2(res[0][k][c], res[1][k][c]))
