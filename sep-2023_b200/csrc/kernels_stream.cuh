@@ -155,7 +155,11 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 // its own 16 bytes, so cp.async.wait_group is the only synchronisation and the registers hold just the stencil windows.
 constexpr int FR_NARR_I = 10, FR_NST_I = 3;                 // interior: 3 stages x 10 arrays x 512 B = 15 KB per warp
 constexpr int FR_NARR_E = 18, FR_NST_E = 2;                 // edge:     2 stages x 18 arrays x 512 B = 18 KB per warp
+#ifdef SW_INTERIOR_ONLY
+constexpr int FR_WARP_BYTES = FR_NARR_I * FR_NST_I * 512;
+#else
 constexpr int FR_WARP_BYTES = FR_NARR_E * FR_NST_E * 512;
+#endif
 constexpr size_t FR_SMEM = (size_t)SW_WPB * FR_WARP_BYTES;  // 72 KB per CTA, 2 CTAs per SM
 enum { FA_VZ = 0, FA_VX, FA_OZZ, FA_OXZ, FA_OXX, FA_LAM, FA_MU, FA_MUA, FA_BYA, FA_BYB,       // rows r+2 (v), r, r-2 (buoyancies)
        FA_PVZZ, FA_PVXZ, FA_PVXX, FA_PVZX, FA_PSZZ, FA_PSXZZ, FA_PSXZX, FA_PSXX };              // CPML memory: rows r (stress side), r-2 (velocity side)
@@ -470,8 +474,12 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_fwd(const KArgs a, co
     const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * FR_WARP_BYTES;
     const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (FR_WARP_BYTES / 16);
     pdl_wait();
+#ifdef SW_INTERIOR_ONLY      // timing experiment: the edge body is not even compiled (wrong results at the edges)
+    stream_fwd_body<false>(a, sa, s, wk, lane, sw, sp);
+#else
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_fwd_body<false>(a, sa, s, wk, lane, sw, sp);
     else stream_fwd_body<true>(a, sa, s, wk, lane, sw, sp);
+#endif
 }
 
 // ================================================================================================
@@ -902,8 +910,12 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, co
     const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * AR_WARP_BYTES;
     const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (AR_WARP_BYTES / 16);
     pdl_wait();
+#ifdef SW_INTERIOR_ONLY
+    stream_adj_body<false>(a, sa, s, wk, lane, stage[threadIdx.x >> 5], sw, sp);
+#else
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_adj_body<false>(a, sa, s, wk, lane, stage[threadIdx.x >> 5], sw, sp);
     else stream_adj_body<true>(a, sa, s, wk, lane, stage[threadIdx.x >> 5], sw, sp);
+#endif
 }
 
 // ================================================================================================
@@ -1175,8 +1187,12 @@ __global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, 
     pdl_wait();
     const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * RC_WARP_BYTES;
     const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (RC_WARP_BYTES / 16);
+#ifdef SW_INTERIOR_ONLY
+    stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);
+#else
     if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_rec_body<false>(a, sa, s, wk, lane, sw, sp);
     else stream_rec_body<true>(a, sa, s, wk, lane, sw, sp);
+#endif
 }
 
 // ================================================================================================
