@@ -22,6 +22,7 @@
 // Arithmetic per cell is the sequence of the baseline kernels (kernels_base.cuh).
 // Reference lines: el_stress.cu:50-87, el_velocity.cu:45-82, utilities.cu:362-392,524-552,593-703.
 #pragma once
+#include <cuda.h>      // CUtensorMap (the type only; the encoder is fetched through cudaGetDriverEntryPoint, nothing links libcuda)
 #include "common.cuh"
 #include "kernels_base.cuh"
 
@@ -41,7 +42,45 @@ struct StreamArgs {
     int nAux;                        // leading CTAs doing the perimeter work
     int nrecMax;                     // largest receiver count over the slots of this batch
     int force;                       // debug/timing only: 1 = every warp takes the interior path (wrong at the edges), 2 = every warp the edge path
+    int tma;                         // interior warps fetch their operand rows with TMA tensor copies (the maps are valid)
 };
+
+// ------------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) operand path of the interior warps.  The state block [slot][array][z][x] and the model block
+// [array][z][x] are described by two tensor maps; one elected lane requests a whole operand row (128 floats = 512 B) per
+// array with ONE instruction and four integer coordinates -- instead of 32 lanes x (16-byte cp.async + 64-bit address
+// arithmetic + row clamping) -- and the bytes land in the same per-warp ring, signalled through one mbarrier per stage.
+// Out-of-range rows / columns are zero-filled by the TMA unit (they only feed unowned or inactive cells).  The copies go
+// L2 -> shared memory without touching L1.
+struct __align__(64) TmaMaps { CUtensorMap state, model, grad; };
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_row4(unsigned dst, const CUtensorMap *map, int x, int z, int arr, int slot, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(z), "r"(arr), "r"(slot), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_row3(unsigned dst, const CUtensorMap *map, int x, int z, int arr, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(z), "r"(arr), "r"(bar) : "memory");
+}
 
 #define Q4(v) {v.x, v.y, v.z, v.w}
 // Register windows are LINEAR: slot j of a 6-slot window holds row (first row of the trip) - 2 + j for the fields that are read
@@ -174,6 +213,11 @@ struct FwdCtx {          // per-warp constants of the march
     unsigned amask;
     bool lown, xps, xpv;
     float c1z, c2z, c1x, c2x, dt;
+    // TMA path (interior warps): tensor maps, the warp's ring base and mbarriers, first column / input buffer / slot coordinates
+    const TmaMaps *tm;
+    unsigned ring_w, bar_s;
+    int x0, cin, slot, lane;
+    bool tma;
 };
 struct FwdWin {          // register windows: old velocities rows r-2 .. r+2, new stresses rows r-4 .. r
     float4 vz[6], vx[6], zz[6], xz[6], xx[6];
@@ -190,6 +234,25 @@ __device__ __forceinline__ void stream_fwd_issue(const FwdCtx &k, const int r, c
     constexpr int NARR = EDGE ? FR_NARR_E : FR_NARR_I;
     const int ld = k.ld, nzA = k.nzA;
     const size_t fsz = k.fsz;
+    if (!EDGE && k.tma) {
+        // every lane has read the stage that is re-armed here (row r - NST) before lane 0 asks the TMA unit to overwrite it
+        __syncwarp();
+        if (k.lane == 0) {
+            const unsigned bar = k.bar_s + 8u * stage, dst = k.ring_w + (unsigned)stage * (NARR * 512);
+            mbar_expect_tx(bar, NARR * 512);
+            tma_row4(dst + FA_VZ * 512, &k.tm->state, k.x0, r + 2, k.cin + F_VZ, k.slot, bar);
+            tma_row4(dst + FA_VX * 512, &k.tm->state, k.x0, r + 2, k.cin + F_VX, k.slot, bar);
+            tma_row4(dst + FA_OZZ * 512, &k.tm->state, k.x0, r, k.cin + F_SZZ, k.slot, bar);
+            tma_row4(dst + FA_OXZ * 512, &k.tm->state, k.x0, r, k.cin + F_SXZ, k.slot, bar);
+            tma_row4(dst + FA_OXX * 512, &k.tm->state, k.x0, r, k.cin + F_SXX, k.slot, bar);
+            tma_row3(dst + FA_LAM * 512, &k.tm->model, k.x0, r, M_LAM, bar);
+            tma_row3(dst + FA_MU * 512, &k.tm->model, k.x0, r, M_MU, bar);
+            tma_row3(dst + FA_MUA * 512, &k.tm->model, k.x0, r, M_MUAVE, bar);
+            tma_row3(dst + FA_BYA * 512, &k.tm->model, k.x0, r - 2, M_BYCA, bar);
+            tma_row3(dst + FA_BYB * 512, &k.tm->model, k.x0, r - 2, M_BYCB, bar);
+        }
+        return;
+    }
     auto rowoff = [&](int row) { return (size_t)min(max(row, 0), nzA - 1) * ld; };   // clamped rows feed inactive / unowned cells only
     const size_t r2 = rowoff(r + 2), r0 = rowoff(r), rq = rowoff(r - 2);
     const unsigned sb = k.ring_s + (unsigned)stage * (NARR * 512);
@@ -210,7 +273,7 @@ __device__ __forceinline__ void stream_fwd_issue(const FwdCtx &k, const int r, c
 
 // one row: request row r + (NST-1), then stress at row r and velocity at row r-2.  U = r's phase in the 6-slot rotation.
 template <bool EDGE, int U>
-__device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const int r, const int stage)
+__device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const int r, const int stage, const unsigned phase = 0)
 {
     constexpr int NARR = EDGE ? FR_NARR_E : FR_NARR_I;
     constexpr int NST = EDGE ? FR_NST_E : FR_NST_I;
@@ -219,7 +282,8 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
     const float c1z = k.c1z, c2z = k.c2z, c1x = k.c1x, c2x = k.c2x, dt = k.dt;
     constexpr int u = U;
     stream_fwd_issue<EDGE>(k, r + (NST - 1), stage == 0 ? NST - 1 : stage - 1);
-    cp_wait<NST - 1>();
+    if (!EDGE && k.tma) mbar_wait(k.bar_s + 8u * stage, phase);     // the TMA unit has delivered this stage's ten rows
+    else cp_wait<NST - 1>();
     const float4 *sb = k.ring_p + stage * (NARR * 32);
     w.vz[(u + 4) % 6] = sb[FA_VZ * 32]; w.vx[(u + 4) % 6] = sb[FA_VX * 32];       // row r+2
     // ---- stress at row r from v rows r-2 .. r+2 (slots u .. u+4)
@@ -381,7 +445,8 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
 
 template <bool EDGE>
 __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs &sa, const int s, const int4 wk, const int lane,
-                                                const unsigned smem_warp, const float4 *ring_ptr)
+                                                const unsigned smem_warp, const float4 *ring_ptr, const TmaMaps *tm = nullptr,
+                                                const unsigned bar_s = 0)
 {
     constexpr int NST = EDGE ? FR_NST_E : FR_NST_I;
     const Dims &d = a.d;
@@ -406,6 +471,16 @@ __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs
     k.zs = a.t.zs[s]; k.xs = a.t.xs[s];
     k.c1z = d.c1z; k.c2z = d.c2z; k.c1x = d.c1x; k.c2x = d.c2x; k.dt = d.dt;
     k.ring_s = smem_warp + lane * 16; k.ring_p = ring_ptr + lane;
+    k.tm = tm; k.ring_w = smem_warp; k.bar_s = bar_s; k.x0 = wk.x - 4; k.cin = p ? S_FWD1 : S_FWD; k.slot = s; k.lane = lane;
+    k.tma = !EDGE && sa.tma != 0 && tm != nullptr;
+    if (k.tma) {      // one mbarrier per ring stage, armed by lane 0 (count 1) and completed by the TMA unit's byte count
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < NST; j++) mbar_init(bar_s + 8u * j, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
     // EDGE: active columns of the quad (x in [2, nx-3]) and whether the quad touches the x CPML strips
     k.amask = 0xf; k.xps = false; k.xpv = false;
     if (EDGE) {
@@ -441,29 +516,37 @@ __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs
     constexpr int UNR = EDGE ? 1 : SW_UNR_FWD;
     static_assert(UNR == 1 || UNR == 2 || UNR == 6, "6-slot windows: 1, 2 or 6 rows per trip");
     int stage = 0;
+    unsigned phase = 0;      // parity of the stage's mbarrier: flips each time the ring wraps
+#define FWD_NEXT_STAGE() do { if (stage == NST - 1) { stage = 0; phase ^= 1u; } else stage++; } while (0)
 #pragma unroll 1
     for (int kk = 0; kk < niter; kk += UNR) {
         const int r = r0 + kk;
-        stream_fwd_row<EDGE, 0>(k, w, r, stage); stage = stage == NST - 1 ? 0 : stage + 1;
-        if (UNR > 1) { stream_fwd_row<EDGE, 1 % UNR>(k, w, r + 1, stage); stage = stage == NST - 1 ? 0 : stage + 1; }
-        if (UNR > 2) { stream_fwd_row<EDGE, 2 % UNR>(k, w, r + 2, stage); stage = stage == NST - 1 ? 0 : stage + 1; }
+        stream_fwd_row<EDGE, 0>(k, w, r, stage, phase); FWD_NEXT_STAGE();
+        if (UNR > 1) { stream_fwd_row<EDGE, 1 % UNR>(k, w, r + 1, stage, phase); FWD_NEXT_STAGE(); }
+        if (UNR > 2) { stream_fwd_row<EDGE, 2 % UNR>(k, w, r + 2, stage, phase); FWD_NEXT_STAGE(); }
         if (UNR > 3) {
-            stream_fwd_row<EDGE, 3 % UNR>(k, w, r + 3, stage); stage = stage == NST - 1 ? 0 : stage + 1;
-            stream_fwd_row<EDGE, 4 % UNR>(k, w, r + 4, stage); stage = stage == NST - 1 ? 0 : stage + 1;
-            stream_fwd_row<EDGE, 5 % UNR>(k, w, r + 5, stage); stage = stage == NST - 1 ? 0 : stage + 1;
+            stream_fwd_row<EDGE, 3 % UNR>(k, w, r + 3, stage, phase); FWD_NEXT_STAGE();
+            stream_fwd_row<EDGE, 4 % UNR>(k, w, r + 4, stage, phase); FWD_NEXT_STAGE();
+            stream_fwd_row<EDGE, 5 % UNR>(k, w, r + 5, stage, phase); FWD_NEXT_STAGE();
         }
         if (UNR < 6) { win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); win_shift<UNR>(w.zz); win_shift<UNR>(w.xz); win_shift<UNR>(w.xx); }
     }
-    cp_wait<0>();
+    if (!EDGE && k.tma) {
+        // the NST - 1 rows requested ahead are still in flight: the warp must not leave (and free its shared memory) before they land
+#pragma unroll
+        for (int j = 0; j < NST - 1; j++) { mbar_wait(k.bar_s + 8u * stage, phase); FWD_NEXT_STAGE(); }
+    } else cp_wait<0>();
+#undef FWD_NEXT_STAGE
 }
 
 #ifndef SW_MINB
 #define SW_MINB 2
 #endif
 // grid: x = nAux + ceil(nWork / SW_WPB), y = slot ; dynamic shared memory FR_SMEM
-__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_fwd(const KArgs a, const StreamArgs sa)
+__global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_fwd(const KArgs a, const StreamArgs sa, const __grid_constant__ TmaMaps tm)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long bars[SW_WPB][4];
     pdl_launch_dependents();
     const int s = blockIdx.y;
     if ((int)blockIdx.x < sa.nAux) { pdl_wait(); stream_fwd_aux(a, sa, s); return; }
@@ -474,10 +557,11 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_fwd(const KArgs a, co
     const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + (threadIdx.x >> 5) * FR_WARP_BYTES;
     const float4 *sp = reinterpret_cast<const float4 *>(smem) + (threadIdx.x >> 5) * (FR_WARP_BYTES / 16);
     pdl_wait();
+    const unsigned bar_s = smem_u32(&bars[threadIdx.x >> 5][0]);
 #ifdef SW_INTERIOR_ONLY      // timing experiment: the edge body is not even compiled (wrong results at the edges)
-    stream_fwd_body<false>(a, sa, s, wk, lane, sw, sp);
+    stream_fwd_body<false>(a, sa, s, wk, lane, sw, sp, &tm, bar_s);
 #else
-    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_fwd_body<false>(a, sa, s, wk, lane, sw, sp);
+    if ((wk.w == 0 || sa.force == 1) && sa.force != 2) stream_fwd_body<false>(a, sa, s, wk, lane, sw, sp, &tm, bar_s);
     else stream_fwd_body<true>(a, sa, s, wk, lane, sw, sp);
 #endif
 }
@@ -890,7 +974,7 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
 __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_adj(const KArgs a, const StreamArgs sa)
 {
     __shared__ __align__(16) float stage[SW_WPB][256];
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     pdl_launch_dependents();
     const int s = blockIdx.y;
     const Dims &d = a.d;
@@ -1177,7 +1261,7 @@ __device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs
 // grid: x = ceil(nWork / SW_WPB), y = slot ; dynamic shared memory RC_SMEM
 __global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, const StreamArgs sa)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     pdl_launch_dependents();
     const int s = blockIdx.y;
     const int wg = (int)blockIdx.x * SW_WPB + ((int)threadIdx.x >> 5);
@@ -1345,7 +1429,7 @@ __device__ __forceinline__ void stream_sp_aux(const KArgs &a, const StreamArgs &
 // grid: x = nAux + ceil(nWork / SW_WPB), y = slot ; dynamic shared memory SP_SMEM ; time step sa.it reads buffer it & 1
 __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_sponge(const KArgs a, const StreamArgs sa)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     pdl_launch_dependents();
     const int s = blockIdx.y;
     const int p = sa.it & 1;

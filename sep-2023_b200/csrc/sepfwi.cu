@@ -65,6 +65,8 @@ struct sepfwi_handle {
     int nStrips = 0;
     bool stream = false;   // register-streaming kernels (kernels = 0 / 3); otherwise the unfused baseline kernels
     bool stream_sponge = false;   // sponge flavour through k_stream_sponge (kernels = 0 / 3)
+    TmaMaps tmaps;                // tensor maps of the state / model / gradient blocks (TMA operand path of the interior warps)
+    bool tma = false;             // ... valid and enabled (SEPFWI_TMA=0 keeps the cp.async path)
     int nSM = 148;
     size_t smem_optin = 0; // largest opt-in dynamic shared memory per block on this device
     bool pdl = true;       // programmatic dependent launch inside the time loops (SEPFWI_PDL=0 disables)
@@ -320,6 +322,46 @@ extern "C" int sepfwi_destroy(sepfwi_handle *h)
     return 0;
 }
 
+// Tensor maps for the TMA operand path: rank-4 view [slot][array][z][x] of the state block, rank-3 views [array][z][x] of the model
+// and (per slot) gradient blocks; boxes of one 128-float row.  The encoder is a driver entry point fetched at run time.
+static bool build_tensor_maps(sepfwi_handle *h)
+{
+    typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn || qr != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    encode_t enc = (encode_t)fn;
+    const Dims &d = h->d;
+    memset(&h->tmaps, 0, sizeof(h->tmaps));
+    const cuuint32_t one[4] = {1, 1, 1, 1};
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)d.ldx, (cuuint64_t)d.nzA, (cuuint64_t)(d.sstride / d.fsz), (cuuint64_t)h->B};
+        const cuuint64_t str[3] = {(cuuint64_t)d.ldx * 4, (cuuint64_t)d.fsz * 4, (cuuint64_t)d.sstride * 4};
+        const cuuint32_t box[4] = {128, 1, 1, 1};
+        if (enc(&h->tmaps.state, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, h->state, dims, str, box, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)d.ldx, (cuuint64_t)d.nzA, (cuuint64_t)NMODEL};
+        const cuuint64_t str[2] = {(cuuint64_t)d.ldx * 4, (cuuint64_t)d.fsz * 4};
+        const cuuint32_t box[3] = {128, 1, 1};
+        if (enc(&h->tmaps.model, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->model, dims, str, box, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
+    if (h->grad) {
+        const cuuint64_t dims[3] = {(cuuint64_t)d.ldx, (cuuint64_t)d.nzA, (cuuint64_t)3 * h->B};
+        const cuuint64_t str[2] = {(cuuint64_t)d.ldx * 4, (cuuint64_t)d.fsz * 4};
+        const cuuint32_t box[3] = {128, 1, 1};
+        if (enc(&h->tmaps.grad, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->grad, dims, str, box, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    } else h->tmaps.grad = h->tmaps.model;
+    return true;
+}
+
 extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle **out)
 {
     if (!pp || !out) return fail(SEPFWI_EINVAL, "null argument");
@@ -492,6 +534,13 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         CU(cudaMemcpy(h->damp, dm.data(), d.fsz * sizeof(float), cudaMemcpyHostToDevice));
     }
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&h->ev[i]));
+    if (h->stream) {
+        // TMA operand path of the forward kernel's interior warps: measured slower than the cp.async ring on every grid (round 2,
+        // profiles/README.md: one row per tensor copy has a longer latency than 32 x 16-byte cp.async, and the march is latency-bound),
+        // so it is opt-in: SEPFWI_TMA=1
+        const char *e = getenv("SEPFWI_TMA");
+        h->tma = e && atoi(e) != 0 && build_tensor_maps(h);
+    }
     *out = h;
     return 0;
 }
@@ -1090,7 +1139,7 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
         StreamArgs sa;
         int rc = stream_plan(h, nb, 0, sa, st);
         if (rc) return rc;
-        sa.fiber = h->p.fiber; sa.save_ring = save_ring ? 1 : 0; sa.nrecMax = mrec;
+        sa.fiber = h->p.fiber; sa.save_ring = save_ring ? 1 : 0; sa.nrecMax = mrec; sa.tma = h->tma ? 1 : 0;
         const int items = (mrec > 0 ? mrec : 0) + (save_ring ? d.ringLen : 0);
         sa.nAux = items > 0 ? std::min(h->nSM, (items + 2 * SW_NT - 1) / (2 * SW_NT)) : 0;      // two items per thread while that stays below one CTA per SM
         dim3 sgrd(sa.nAux + (sa.nWork + SW_WPB - 1) / SW_WPB, nb);
@@ -1098,7 +1147,7 @@ static int run_forward(sepfwi_handle *h, int nb, int mrec, int mask, bool save_r
             const bool pr = it < h->prof_steps;
             sa.it = it; sa.mask = (it >= 1 && mrec > 0) ? mask : 0;
             cudaError_t le = cudaSuccess;
-            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (le = launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), FR_SMEM + h->smem_pad, st, h->pdl, a, sa)));
+            LAUNCH(h, SEPFWI_K_STREAM_FWD, pr, st, (le = launch_pdl(k_stream_fwd, sgrd, dim3(SW_NT), FR_SMEM + h->smem_pad, st, h->pdl, a, sa, h->tmaps)));
             CU(le);
         }
         const int par = (d.nSteps - 1) & 1;   // buffer that holds the final state

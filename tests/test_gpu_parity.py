@@ -583,3 +583,18 @@ def test_sponge_flavour_streaming_kernel_matches_unfused_kernels(nx, nb):
         for c in ("pr", "vx", "vz", "ett", "exx", "ezz", "exz"):
             assert np.abs(res[1][k][c]).max() > 0
             assert rel_l2(res[0][k][c], res[1][k][c]) < 1e-5, (k, c, rel_l2(res[0][k][c], res[1][k][c]))
+
+
+def test_tma_operand_path_of_the_forward_kernel(monkeypatch):
+    """SEPFWI_TMA=1: the interior warps of k_stream_fwd fetch their operand rows with cp.async.bulk.tensor (one elected lane, tensor
+    maps over the state / model blocks, one mbarrier per ring stage) instead of per-lane cp.async -- same bits as the default path
+    (the arithmetic is untouched; out-of-range rows are zero-filled instead of clamped and only feed unowned cells)."""
+    prob = problems.medium()
+    base = _run_both(prob, 3)
+    monkeypatch.setenv("SEPFWI_TMA", "1")
+    tma = _run_both(prob, 3)
+    for sid in range(prob.nshots):
+        for c in ("pr", "vx", "vz", "ett"):
+            assert np.array_equal(tma[0][sid][c], base[0][sid][c]), (sid, c)
+    for k in ("glam", "gmu", "grho"):
+        assert np.array_equal(tma[1][k], base[1][k]), k
