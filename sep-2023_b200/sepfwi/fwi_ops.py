@@ -46,18 +46,22 @@ def _torch():
 def auto_batch(nz, nx, nPad, nSteps, nrec, nPml, with_adjoint, nshots, device, params=None):
     """Concurrent shots per launch: enough to give every launch a few million cells, within memory.  The bytes one slot
     costs come from the library (sepfwi_bytes_per_slot: state block, boundary ring, traces, gradients, tables) plus the
-    device-cached observed data of the shot; at most 60 % of what is free now."""
+    device-cached observed data of the shot; at most 70 % of what is free now, split into equal batches."""
     torch = _torch()
     cells = float((nz - nPad) * nx)
-    B = min(32, int(4.0e6 / cells) + 1)      # small grids: one launch for the whole survey beats two (whole waves of latency-bound warps)
+    # measured on B200 (C3 grid, 730 k cells): 5.7 / 6.6 / 7.2 / 7.8 shot-gradients/s at 8 / 16 / 32 / 64 shots per launch -- the tails of
+    # every launch and the slow CPML items amortise over the batch; small grids: one launch for the whole survey beats two
+    B = min(64, int(5.0e7 / cells) + 1)
     if params is None:
         params = _lib.Params(int(nz), int(nx), int(nPml), int(nPad), int(nSteps), 1.0, 1.0, 1.0, 1.0, 0, 0, 1, max(1, int(nrec)),
                              1 if with_adjoint else 0, 0, 0)
     per = float(_lib.lib().sepfwi_bytes_per_slot(params)) + 4.0 * nrec * nSteps
     free = torch.cuda.mem_get_info(device)[0]
-    while B > 1 and per * B > 0.6 * free:
+    while B > 1 and per * B > 0.7 * free:
         B -= 1
-    return max(1, min(B, nshots))
+    B = max(1, min(B, nshots))
+    nbatch = -(-nshots // B)
+    return -(-nshots // nbatch)          # equal batches: 64 shots at a limit of 59 run as 32 + 32, not 59 + 5
 
 
 def _prop(para, device, with_adjoint, nrec, nshots):

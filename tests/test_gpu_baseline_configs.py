@@ -171,3 +171,45 @@ def test_c4_vertical_fiber_gradient_against_oracle():
     assert rel_l2(r["gmu"], gm) < 2e-4
     assert rel_l2(r["grho"], gd) < 2e-4
     assert rel_l2(np.stack(r["gstf"]), gs) < 2e-4
+
+
+def test_cufd_dropin_scratch_outputs_against_live_reference(tmp_path):
+    """`scratch_dir_name` side channel (libCUFD.cu:731-751): Residual_Shot / Syn_Shot / CondObs_Shot{id}.bin -- the pressure residual
+    (sample 0 zeroed), the synthetic pressure and the observed pressure as loaded -- written by sepfwi_cufd and by the reference's
+    cufd on the same inputs."""
+    from sepfwi import _lib, fwi_utils as ft
+    ref_cufd = _ref()
+    prob = problems.tiny()
+    ids = np.arange(prob.nshots, dtype=np.int32)
+    out = {}
+    for who in ("ref", "mine"):
+        work = str(tmp_path / who)
+        os.makedirs(work)
+        para, survey, data, scratch = work + "/para.json", work + "/survey.json", work + "/d", work + "/scratch"
+        ft.paraGen(prob.nz, prob.nx, prob.dz, prob.dx, prob.nSteps, prob.dt, prob.f0, prob.nPml, prob.nPad, para, survey, data,
+                   scratch_dir_name=scratch)
+        ft.surveyGen(prob.z_src, prob.x_src, prob.z_rec, prob.x_rec, survey)
+        stf = np.ascontiguousarray(prob.stf, np.float32)
+
+        def call(calc_id, model):
+            if who == "ref":
+                return ref_cufd.cufd(calc_id, *model, stf, ids, para)
+            lam, mu, den = (np.ascontiguousarray(a, np.float32) for a in model)
+            J = np.zeros(1, np.float32)
+            g = [np.zeros_like(lam) for _ in range(3)]
+            gs = np.zeros_like(stf)
+            p = lambda a: a.ctypes.data
+            _lib.check(_lib.lib().sepfwi_cufd(p(J), p(g[0]), p(g[1]), p(g[2]), p(gs), p(lam), p(mu), p(den), p(stf), calc_id, 0, ids.size,
+                                               p(ids), para.encode()))
+            return float(J[0]),
+        call(2, prob.true)
+        call(1, prob.start)
+        out[who] = {n: [np.fromfile(os.path.join(scratch, "%s_Shot%d.bin" % (n, i)), np.float32) for i in ids]
+                    for n in ("Residual", "Syn", "CondObs")}
+    n = len(prob.x_rec) * prob.nSteps
+    for name in ("Residual", "Syn", "CondObs"):
+        for i in ids:
+            assert out["mine"][name][i].size == n == out["ref"][name][i].size
+            assert np.abs(out["ref"][name][i]).max() > 0
+            assert rel_l2(out["mine"][name][i], out["ref"][name][i]) < TOL_REF_TRACE, (name, i)
+    _lib.lib().sepfwi_cufd_clear_cache()
