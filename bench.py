@@ -189,8 +189,9 @@ def reference_arm(args):
     w = workload(args.workload)
     grad = args.workload == "c3"
     cores = os.cpu_count() or 1
-    # bounded sample: a tenth of the shot's time loop per step (c3 gradient: ~3 s on 16 cores), the whole run within minutes
-    nt_sample = 401 if w["live"] < 2e6 else 21
+    # bounded sample: a twentieth of the shot's time loop per step (c3 gradient: ~5 s on 16 cores; the CPU restatement of the
+    # reverse-time half emulates the reference's atomics and is ~5x slower per sweep than its forward half), the whole run within minutes
+    nt_sample = 201 if w["live"] < 2e6 else 21
     cpu_sample(w, 21, cores, grad)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_sample(w, nt_sample, cores, grad)
