@@ -26,7 +26,7 @@ enum { P_VZ_Z = 0, P_VZ_X = 1, P_VX_Z = 2, P_VX_X = 3, P_SZZ_Z = 4, P_SXZ_X = 5,
 // State block of one slot (array index; every array has fsz floats):
 //   S_FWD / S_FWD1    forward fields, ping-pong pair (the baseline kernels update S_FWD in place)
 //   S_FPSI            forward CPML memory: P_V* (stress update) and P_S* (velocity update)
-//   S_FPSIV1          second copy of the four P_V* for the fused kernel's out-of-place update
+//   S_FPSIV1          second copy of the four P_V* for the streaming forward kernel's out-of-place update (halo recompute reads the old one)
 //   S_ADJ / S_ADJ1    adjoint fields, ping-pong pair
 //   S_APSI / S_APSI1  adjoint CPML memory, ping-pong pair
 enum { S_FWD = 0, S_FWD1 = NFIELD, S_FPSI = 2 * NFIELD, S_FPSIV1 = 2 * NFIELD + NPSI, NSTATE_FWD = 2 * NFIELD + NPSI + 4,

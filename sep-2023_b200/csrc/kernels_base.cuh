@@ -1,7 +1,7 @@
 // kernels_base.cuh -- baseline (unfused) sm_100a kernels: one launch per half step.
 //
 // These are the first correct CUDA path and stay in the library as the on-GPU
-// cross-check of the fused kernels (sepfwi_params.kernels = 1).  Written from the
+// cross-check of the streaming / resident kernels (sepfwi_params.kernels = 1).  Written from the
 // numerical specification in SURVEY.md App. A; reference lines are cited per kernel
 // (paths under DAS_Waveform_Inversion/Ops/FWI/Src/).
 //

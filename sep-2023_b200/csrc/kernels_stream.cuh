@@ -38,7 +38,6 @@ struct StreamArgs {
     int q, pa;                       // backward: forward buffer holding state it+1, adjoint buffer holding adj(it+1)
     const int4 *work;                // work list, one entry per warp: {x0 = first owned column, z0, z1 = owned rows [z0, z1), 1 if edge}
     int nWork;                       //   edge entries (CPML strips / inactive rim) come first: they are the slow ones
-    int nEdge;                       //   number of edge entries
     int nAux;                        // leading CTAs doing the perimeter work
     int nrecMax;                     // largest receiver count over the slots of this batch
     int force;                       // debug/timing only: 1 = every warp takes the interior path (wrong at the edges), 2 = every warp the edge path

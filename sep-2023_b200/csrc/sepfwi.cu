@@ -873,7 +873,6 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     std::stable_sort(inner.begin(), inner.end(), [&](const int4 &p, const int4 &q) {
         const int hp = heavy[p.x / SW_OWN] ? 0 : 1, hq = heavy[q.x / SW_OWN] ? 0 : 1;
         return hp != hq ? hp < hq : p.y < q.y; });
-    const int nEdgeItems = (int)edge.size();
     edge.insert(edge.end(), inner.begin(), inner.end());
     if (items_out) { *items_out = edge; return 0; }      // host-only planning (sepfwi_plan_stream): nothing is uploaded
     if (edge.size() > h->work_cap[which]) {
@@ -889,7 +888,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     } else if (h->plan_sig[which]) CU(cudaStreamSynchronize(st));      // the pinned mirror may still be in flight / the list in use
     memcpy(h->work_host[which], edge.data(), edge.size() * sizeof(int4));
     CU(cudaMemcpyAsync(h->work[which], h->work_host[which], edge.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-    sa.work = h->work[which]; sa.nWork = (int)edge.size(); sa.nEdge = nEdgeItems;
+    sa.work = h->work[which]; sa.nWork = (int)edge.size();
     h->plan_sa[which] = sa; h->plan_sig[which] = want;
     return 0;
 }

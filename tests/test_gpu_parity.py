@@ -46,8 +46,8 @@ def test_forward_traces_match_oracle(mk, batch):
 
 
 @pytest.mark.parametrize("mk,batch", [(problems.tiny, 2), (problems.small, 3), (lambda: problems.tiny(fiber=1), 1)])
-def test_fused_kernels_match_baseline_kernels(mk, batch):
-    """Default (fused, ping-pong, halo-recompute) path vs the unfused baseline kernels: same per-cell
+def test_default_path_matches_baseline_kernels(mk, batch):
+    """Default path (resident forward loop / streaming kernels: ping-pong state, halo recompute) vs the unfused baseline kernels: same per-cell
     arithmetic, so forward traces and gradients agree to rounding of differently contracted FMAs."""
     O, Propagator, ShotSpec = _mods()
     prob = mk()

@@ -43,7 +43,7 @@ def run(name, batch, grad, nsteps, profile=False):
             pr = P.profile()
             print("     per-kernel us:", {k: round(1e3 * ms / n, 1) for k, (ms, n) in pr.items()})
             fk = [k for k in ("stream_fwd", "stress_fwd", "velocity_fwd") if k in pr]
-            bk = [k for k in ("stream_bwd", "stream_recon", "stream_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in pr]
+            bk = [k for k in ("stream_recon", "stream_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in pr]
             tf = sum(pr[k][0] / pr[k][1] for k in fk) * 1e-3
             print("     forward step: %.1f us -> %.0f GB/s algorithmic (52 B/cell) = %.2f of 6451" % (tf * 1e6, 52 * w["live"] / tf / 1e9, 52 * w["live"] / tf / 1e9 / 6451.2))
             if bk:
@@ -52,7 +52,7 @@ def run(name, batch, grad, nsteps, profile=False):
                 print("     backward step: %.1f us -> %.0f GB/s algorithmic = %.2f of 6451" % (tb * 1e6, ab, ab / 6451.2))
 
 
-print("lib:", os.environ.get("SEPFWI_LIB", "default"), "kernels", kernels, "merge", os.environ.get("SEPFWI_MERGE_BWD", "default"), flush=True)
+print("lib:", os.environ.get("SEPFWI_LIB", "default"), "kernels", kernels, "TMA", os.environ.get("SEPFWI_TMA", "0"), flush=True)
 which = sys.argv[3].split(",") if len(sys.argv) > 3 else ["c2", "c2x8", "c3", "c3x8", "ref", "c5s"]
 if "c2" in which: run("c2", 1, False, nt)
 if "c2x8" in which: run("c2", 8, False, nt)
