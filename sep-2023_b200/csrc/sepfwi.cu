@@ -810,8 +810,64 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 3 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 4; };
     int nInnerStrips = 0;
     for (int sx = 0; sx < nStrips; sx++) nInnerStrips += strip_inner(sx) ? 1 : 0;
-    // cost model: whole waves of `conc` warps, each wave as long as its longest item.  Interior items run
-    // 6 ceil((Lz+4)/6) rows, edge items Le + 4 rows at edge_cost x the cost per row.
+    // Two regimes (round 2, calibrated with tools/sweep_plan.sh on the B200):
+    //  * the batch's working set stays in the 126 MB L2 (one shot of the BASELINE grids, the reference's 19-shot experiment): the
+    //    launch is one to two waves of latency-bound items -- a CPML row of the adjoint sweep takes ~2.5 us against 0.4 us for an
+    //    interior row -- and what counts is when the last CTA finishes.  Cost = the makespan of a list-scheduling simulation of
+    //    the launch (CTAs of four items in launch order onto nSM x 2 CTA slots, item cost = rows x cost per row).
+    //  * beyond L2 (batches, the 8000 x 2000 grid): HBM throughput, several waves; the round-1 wave model below.
+    static const double narr[3] = {20.0, 26.0, 20.0};                 // arrays a launch touches per cell
+    const double ws = (double)nb * d.nzA * d.nx * 4.0 * narr[model];
+    const double bl = std::min(1.0, std::max(0.0, (ws - 60.0e6) / 140.0e6));      // 0: L2-resident ... 1: HBM-bound
+    int best = 8, Le = 8;
+    double bestc = 1e300;
+    if (bl < 0.5) {
+        static const double rho_res[3] = {2.0, 3.0, 4.0};             // cost of an edge row in interior rows (latency regime)
+        const double ci = 1.0 + 2.0 * bl, rho = rho_res[model] * (1.0 + 0.25 * bl), P = 3.0;      // P: prologue, in rows
+        const int nslots = h->nSM * (h->warps_per_sm / SW_WPB);
+        // (measured: below 8 interior / 2 edge rows per item the 4-row halo and the prologue only add work)
+        static const int lzs[] = {8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128};
+        static const int les2[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+        std::vector<float> cost;
+        std::vector<double> slot(nslots);
+        for (int Lz : lzs)
+            for (int le : les2) {
+                cost.clear();
+                auto piece = [&](int z0, int z1, int L, bool is_edge) {
+                    const int n = (z1 - z0 + L - 1) / L;
+                    for (int c = 0; c < n; c++) {
+                        const int a0 = z0 + (int)((long long)(z1 - z0) * c / n), a1 = z0 + (int)((long long)(z1 - z0) * (c + 1) / n);
+                        int rows = a1 - a0;
+                        if (model == 1) {      // reconstruction: rows outside interior + ring are skipped, items without any return at once
+                            rows = std::max(0, std::min(a1, d.z1 + 3) - std::max(a0, d.nPml - 2));
+                            if (rows == 0) { cost.push_back(0.2f); continue; }
+                        }
+                        cost.push_back(is_edge ? (float)((rows + 4 + P) * rho) : (float)((((rows + 4 + 1) / 2) * 2 + P) * ci));
+                    }
+                };
+                for (int sx = 0; sx < nStrips; sx++) { piece(0, zi0, le, true); piece(zi1, d.nzA, le, true); }
+                for (int sx = 0; sx < nStrips; sx++) if (!strip_inner(sx)) piece(zi0, zi1, le, true);
+                for (int sx = 0; sx < nStrips; sx++) if (strip_inner(sx)) piece(zi0, zi1, Lz, false);
+                // list scheduling: every CTA goes to the slot that frees first (min-heap of finish times)
+                std::fill(slot.begin(), slot.end(), 0.0);
+                double end = 0.0;
+                auto cmp = [](double x, double y) { return x > y; };
+                std::make_heap(slot.begin(), slot.end(), cmp);
+                for (int b = 0; b < nb; b++)
+                    for (size_t i = 0; i < cost.size(); i += SW_WPB) {
+                        float dmax = 0.f;
+                        for (size_t j = i; j < std::min(cost.size(), i + SW_WPB); j++) dmax = std::max(dmax, cost[j]);
+                        std::pop_heap(slot.begin(), slot.end(), cmp);
+                        const double t = slot.back() + dmax;
+                        slot.back() = t;
+                        std::push_heap(slot.begin(), slot.end(), cmp);
+                        end = std::max(end, t);
+                    }
+                if (end < bestc - 1e-9) { bestc = end; best = Lz; Le = le; }
+            }
+    } else {
+    // wave model: whole waves of `conc` warps, each wave as long as its longest item.  Interior items run
+    // 2 ceil((Lz+4)/2) rows, edge items Le + 4 rows at edge_cost x the cost per row.
     // measured cost of an edge row relative to an interior row: in throughput (many waves, HBM-bound) and in latency
     // (a lone warp per scheduler: shorter look-ahead, register moves); the CPML rows of the adjoint sweep are the expensive ones
     static const double edge_thr[3] = {1.15, 1.1, 1.8}, edge_lat[3] = {2.0, 1.6, 2.5};
@@ -821,8 +877,6 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
         n_in = (double)nInnerStrips * nch;
         n_ed = (double)(nStrips - nInnerStrips) * nche + (double)nStrips * ntb;
     };
-    int best = 8, Le = 8;
-    double bestc = 1e300;
     static const int les[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128};
     for (int Lz = 2; Lz <= 128; Lz += 6)
         for (int le : les) {
@@ -832,8 +886,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
             const double work = (n_in * it_i + n_ed * it_e) * nb * mult / conc, longest = std::max(it_i, (le + 4 + 3.0) * edge_latc);
             // one wave or less: the longest item is the time; many waves: throughput plus half an item of tail
             double c = std::max(longest, work + 0.5 * longest);
-            // a few waves: whole waves of latency-bound items (measured: 19 shots of the 192 x 265 grid at 63 items per shot are
-            // 1197 items = 2 waves and 91 us, at 48 items per shot 1 wave and 64 us).  The reconstruction kernel's items outside
+            // a few waves: whole waves of latency-bound items.  The reconstruction kernel's items outside
             // the interior + ring return at once and do not occupy a slot.
             const double live = model == 1 ? std::min(1.0, (double)(d.nzA - 2 * d.nPml + 4) / d.nzA) : 1.0;
             const double waves = ceil((n_in + n_ed) * nb * mult * live / conc);
@@ -841,8 +894,9 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
                 c = std::max(c, waves * (n_in * it_i + n_ed * (le + 4 + 3.0) * edge_latc) / (n_in + n_ed));
             if (c < bestc - 1e-9) { bestc = c; best = Lz; Le = le; }
         }
-    if (h->tune_lz >= 2) best = h->tune_lz;
-    if (h->tune_lze >= 2) Le = h->tune_lze;
+    }
+    if (h->tune_lz >= 1) best = h->tune_lz;
+    if (h->tune_lze >= 1) Le = h->tune_lze;
     sa.force = h->tune_force;
     if (h->plan_debug) fprintf(stderr, "stream_plan[%d]: nb %d Lz %d Le %d cost %.1f\n", which, nb, best, Le, bestc);
     std::vector<int4> edge, inner;

@@ -61,5 +61,5 @@ if "c3x8" in which: run("c3", 8, True, nt, profile=True)
 if "c3x16" in which: run("c3", 16, True, nt, profile=True)
 if "c3x32" in which: run("c3", 32, True, nt, profile=True)
 if "c3x64" in which: run("c3", 64, True, nt, profile=True)
-if "ref" in which: run("ref", 19, True, nt)
+if "ref" in which: run("ref", 19, True, nt, profile=True)
 if "c5s" in which: run("c5s", 1, True, 60, profile=True)
