@@ -29,7 +29,10 @@
 namespace sepfwi {
 
 constexpr int SW_OWN = 120;          // columns owned by one warp (30 quads)
-constexpr int SW_WPB = 4;            // warps per CTA
+#ifndef SW_WPB_
+#define SW_WPB_ 4
+#endif
+constexpr int SW_WPB = SW_WPB_;      // warps per CTA
 constexpr int SW_NT = SW_WPB * 32;
 
 struct StreamArgs {
@@ -271,7 +274,8 @@ __device__ __forceinline__ void stream_fwd_issue(const FwdCtx &k, const int r, c
 }
 
 // one row: request row r + (NST-1), then stress at row r and velocity at row r-2.  U = r's phase in the 6-slot rotation.
-template <bool EDGE, int U>
+// PB: second phase of the row -- 0 always, 1 never (the chunk's lead-in rows: nothing of it would be kept), 2 warp-uniform test
+template <bool EDGE, int U, int PB>
 __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const int r, const int stage, const unsigned phase = 0)
 {
     constexpr int NARR = EDGE ? FR_NARR_E : FR_NARR_I;
@@ -368,7 +372,7 @@ __device__ __forceinline__ void stream_fwd_row(const FwdCtx &k, FwdWin &w, const
         }
     }
     // ---- velocity at row q = r-2 : szz rows q-1..q+2, sxz rows q-2..q+1, sxx row q (stress row r-j lives in slot u+4-j)
-    {
+    if (PB == 0 || (PB == 2 && (r - 2 >= k.zc0) && (r - 2 < k.zc1))) {      // warp-uniform: on the chunk's four lead-in rows (and the surplus row of the last trip) nothing of this phase is kept
         const int q = r - 2;
         const float4 p0 = w.zz[(u + 1) % 6], p1 = w.zz[(u + 2) % 6], p2 = w.zz[(u + 3) % 6], p3 = w.zz[(u + 4) % 6];
         const float4 q0 = w.xz[u % 6], q1 = w.xz[(u + 1) % 6], q2 = w.xz[(u + 2) % 6], q3 = w.xz[(u + 3) % 6];
@@ -513,22 +517,29 @@ __device__ __forceinline__ void stream_fwd_body(const KArgs &a, const StreamArgs
     // UNR rows per trip, then the windows move down UNR slots; surplus rows of the last trip are computed and dropped.
     // Edge warps: one row per trip (their body is much longer).
     constexpr int UNR = EDGE ? 1 : SW_UNR_FWD;
-    static_assert(UNR == 1 || UNR == 2 || UNR == 6, "6-slot windows: 1, 2 or 6 rows per trip");
+    static_assert(UNR == 1 || UNR == 2, "one or two rows per trip");
+    // the first four rows only fill the windows of the second phase (its row q = r - 2 is not owned yet): interior warps run them
+    // in a lead-in loop without that phase, edge warps (one long body) test per row
+    constexpr int PBM = EDGE ? 2 : 0, PBL = EDGE ? 2 : 1;
     int stage = 0;
     unsigned phase = 0;      // parity of the stage's mbarrier: flips each time the ring wraps
 #define FWD_NEXT_STAGE() do { if (stage == NST - 1) { stage = 0; phase ^= 1u; } else stage++; } while (0)
+    int kk = 0;
+    if (!EDGE) {
 #pragma unroll 1
-    for (int kk = 0; kk < niter; kk += UNR) {
-        const int r = r0 + kk;
-        stream_fwd_row<EDGE, 0>(k, w, r, stage, phase); FWD_NEXT_STAGE();
-        if (UNR > 1) { stream_fwd_row<EDGE, 1 % UNR>(k, w, r + 1, stage, phase); FWD_NEXT_STAGE(); }
-        if (UNR > 2) { stream_fwd_row<EDGE, 2 % UNR>(k, w, r + 2, stage, phase); FWD_NEXT_STAGE(); }
-        if (UNR > 3) {
-            stream_fwd_row<EDGE, 3 % UNR>(k, w, r + 3, stage, phase); FWD_NEXT_STAGE();
-            stream_fwd_row<EDGE, 4 % UNR>(k, w, r + 4, stage, phase); FWD_NEXT_STAGE();
-            stream_fwd_row<EDGE, 5 % UNR>(k, w, r + 5, stage, phase); FWD_NEXT_STAGE();
+        for (; kk < 4; kk += UNR) {
+            const int r = r0 + kk;
+            stream_fwd_row<EDGE, 0, PBL>(k, w, r, stage, phase); FWD_NEXT_STAGE();
+            if (UNR > 1) { stream_fwd_row<EDGE, 1 % UNR, PBL>(k, w, r + 1, stage, phase); FWD_NEXT_STAGE(); }
+            win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); win_shift<UNR>(w.zz); win_shift<UNR>(w.xz); win_shift<UNR>(w.xx);
         }
-        if (UNR < 6) { win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); win_shift<UNR>(w.zz); win_shift<UNR>(w.xz); win_shift<UNR>(w.xx); }
+    }
+#pragma unroll 1
+    for (; kk < niter; kk += UNR) {
+        const int r = r0 + kk;
+        stream_fwd_row<EDGE, 0, PBM>(k, w, r, stage, phase); FWD_NEXT_STAGE();
+        if (UNR > 1) { stream_fwd_row<EDGE, 1 % UNR, PBM>(k, w, r + 1, stage, phase); FWD_NEXT_STAGE(); }
+        win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); win_shift<UNR>(w.zz); win_shift<UNR>(w.xz); win_shift<UNR>(w.xx);
     }
     if (!EDGE && k.tma) {
         // the NST - 1 rows requested ahead are still in flight: the warp must not leave (and free its shared memory) before they land
@@ -664,7 +675,7 @@ __device__ __forceinline__ void stream_adj_issue(const AdjCtx &k, const int r, c
     cp_commit();
 }
 
-template <bool EDGE, int U>
+template <bool EDGE, int U, int PB>
 __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const int r, const int stage)
 {
     const int ld = k.ld, nzA = k.nzA;
@@ -723,8 +734,13 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             }
             if (zp) {
                 const float *pz0 = k.psrc + (size_t)P_VX_Z * fsz + ro, *pz1 = k.psrc + (size_t)P_VZ_Z * fsz + ro;
+#ifdef EXP_NO_AZ
+                const float4 t3 = k.xany ? ldq(pz0 + ld) : sb[AZ_PVXZ * 32], s3 = k.xany ? ldq(pz1 + 2 * ld) : sb[AZ_PVZZ * 32];
+                const float4 t0 = t3, t1 = t3, t2 = t3, s0 = s3, s1 = s3, s2 = s3;
+#else
                 const float4 t0 = ldq(pz0 - 2 * ld), t1 = ldq(pz0 - ld), t2 = ldq(pz0), t3 = k.xany ? ldq(pz0 + ld) : sb[AZ_PVXZ * 32];
                 const float4 s0 = ldq(pz1 - ld), s1 = ldq(pz1), s2 = ldq(pz1 + ld), s3 = k.xany ? ldq(pz1 + 2 * ld) : sb[AZ_PVZZ * 32];
+#endif
                 const float a0[4] = Q4(t0), a1[4] = Q4(t1), a2[4] = Q4(t2), a3[4] = Q4(t3), b0[4] = Q4(s0), b1[4] = Q4(s1), b2[4] = Q4(s2), b3[4] = Q4(s3);
 #pragma unroll
                 for (int c = 0; c < 4; c++) { dpx[c] += azh * -DZ4(a0[c], a1[c], a2[c], a3[c]); dpz[c] += az * -DZ4(b0[c], b1[c], b2[c], b3[c]); }
@@ -744,7 +760,11 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             // neighbouring warps that recompute the same halo cells write the same values.
             w.qxx[2] = zero4; w.qxz[2] = zero4;      // what phase B would read back from pdst two rows later (zero outside the x strips)
             if (xl || zp) {
+#ifdef EXP_NO_BAR
+                const float4 bar4 = sb[AA_BYA * 32], bbr4 = sb[AA_BYB * 32];
+#else
                 const float4 bar4 = ldq(k.m + M_BYCA * fsz + ro), bbr4 = ldq(k.m + M_BYCB * fsz + ro);
+#endif
                 const float bar[4] = Q4(bar4), bbr[4] = Q4(bbr4);
                 unsigned vm = k.amask;                               // columns with a complete window that are active
                 if (k.lane == 0) vm &= 0xcu;
@@ -787,7 +807,7 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
     }
     if (EDGE) __syncwarp();      // phase B reads CPML memory written by other lanes of this warp
     // ---- phase B: adjoint stresses at row q = r-2 from v^z rows q-2..q+1, v^x rows q-1..q+2 (row r-j lives in slot u+4-j)
-    {
+    if (PB == 0 || (PB == 2 && (r - 2 >= k.zc0) && (r - 2 < k.zc1))) {      // warp-uniform: nothing of this phase is kept for a row the chunk does not own
         const int q = r - 2;
         const float4 v0 = w.vz[u % 6], v1 = w.vz[(u + 1) % 6], v2 = w.vz[(u + 2) % 6], v3 = w.vz[(u + 3) % 6];
         const float4 u0 = w.vx[(u + 1) % 6], u1 = w.vx[(u + 2) % 6], u2 = w.vx[(u + 3) % 6], u3 = w.vx[(u + 4) % 6];
@@ -832,8 +852,12 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             }
             if (zpq) {
                 const float *pz0 = k.pdst + (size_t)P_SXZ_Z * fsz + ro, *pz1 = k.pdst + (size_t)P_SZZ_Z * fsz + ro;
+#ifdef EXP_NO_BZ
+                const float4 t0 = w.vz[0], t1 = w.vz[1], t2 = w.vz[2], t3 = w.vz[3], s0 = w.vx[0], s1 = w.vx[1], s2 = w.vx[2], s3 = w.vx[3];
+#else
                 const float4 t0 = ldq_rw(pz0 - ld), t1 = ldq_rw(pz0), t2 = ldq_rw(pz0 + ld), t3 = ldq_rw(pz0 + 2 * ld);
                 const float4 s0 = ldq_rw(pz1 - 2 * ld), s1 = ldq_rw(pz1 - ld), s2 = ldq_rw(pz1), s3 = ldq_rw(pz1 + ld);
+#endif
                 const float a0[4] = Q4(t0), a1[4] = Q4(t1), a2[4] = Q4(t2), a3[4] = Q4(t3), b0[4] = Q4(s0), b1[4] = Q4(s1), b2[4] = Q4(s2), b3[4] = Q4(s3);
 #pragma unroll
                 for (int c = 0; c < 4; c++) { dxz[c] += az * -DZ4(a0[c], a1[c], a2[c], a3[c]); dzz[c] = azh * -DZ4(b0[c], b1[c], b2[c], b3[c]); }
@@ -851,12 +875,20 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             }
             // CPML memory of the adjoint stresses: owner-only, strips nPml + 2 wide (el_stress_adj.cu:67-72,88-95)
             if ((xl2 || zst) && k.lown) {
+#ifdef EXP_NO_BM
+                const float4 l4 = sb[AA_LAM * 32], m4 = sb[AA_MU * 32], a4 = sb[AA_MUA * 32];
+#else
                 const float4 l4 = ldq(k.m + M_LAM * fsz + ro), m4 = ldq(k.m + M_MU * fsz + ro), a4 = ldq(k.m + M_MUAVE * fsz + ro);
+#endif
                 const float lq[4] = Q4(l4), mq[4] = Q4(m4), maq[4] = Q4(a4);
                 if (xl2) {
                     const float4 f0 = ldq_c(k.cxa + C_BH * ld), f1 = ldq_c(k.cxa + C_B * ld);
                     const float bxh[4] = Q4(f0), bx[4] = Q4(f1);
+#ifdef EXP_NO_BO
+                    const float4 o0 = w.vz[1], o1 = w.vx[1];
+#else
                     const float4 o0 = ldq(k.psrc + (size_t)P_VZ_X * fsz + ro), o1 = ldq(k.psrc + (size_t)P_VX_X * fsz + ro);
+#endif
                     float n0[4] = Q4(o0), n1[4] = Q4(o1);
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
@@ -869,7 +901,11 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
                     stq(k.pdst + (size_t)P_VZ_X * fsz + ro, mk4(n0)); stq(k.pdst + (size_t)P_VX_X * fsz + ro, mk4(n1));
                 }
                 if (zst) {
+#ifdef EXP_NO_BO
+                    const float4 o0 = w.vz[2], o1 = w.vx[2];
+#else
                     const float4 o0 = ldq(k.psrc + (size_t)P_VX_Z * fsz + ro), o1 = ldq(k.psrc + (size_t)P_VZ_Z * fsz + ro);
+#endif
                     float n0[4] = Q4(o0), n1[4] = Q4(o1);
 #pragma unroll
                     for (int c = 0; c < 4; c++)
@@ -950,19 +986,24 @@ __device__ __forceinline__ void stream_adj_body(const KArgs &a, const StreamArgs
     for (int j = 0; j < (EDGE ? AR_NST_E : AR_NST) - 1; j++) stream_adj_issue<EDGE>(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
     constexpr int UNR = EDGE ? 1 : SW_UNR_ADJ, NST = EDGE ? AR_NST_E : AR_NST;
-    int stg = 0;
+    static_assert(UNR == 1 || UNR == 2, "one or two rows per trip");
+    constexpr int PBM = EDGE ? 2 : 0, PBL = EDGE ? 2 : 1;      // see stream_fwd_body
+    int stg = 0, kk = 0;
+    if (!EDGE) {
 #pragma unroll 1
-    for (int kk = 0; kk < niter; kk += UNR) {
-        const int r = r0 + kk;
-        stream_adj_row<EDGE, 0>(k, w, r, stg); stg = stg == NST - 1 ? 0 : stg + 1;
-        if (UNR > 1) { stream_adj_row<EDGE, 1 % UNR>(k, w, r + 1, stg); stg = stg == NST - 1 ? 0 : stg + 1; }
-        if (UNR > 2) { stream_adj_row<EDGE, 2 % UNR>(k, w, r + 2, stg); stg = stg == NST - 1 ? 0 : stg + 1; }
-        if (UNR > 3) {
-            stream_adj_row<EDGE, 3 % UNR>(k, w, r + 3, stg); stg = stg == NST - 1 ? 0 : stg + 1;
-            stream_adj_row<EDGE, 4 % UNR>(k, w, r + 4, stg); stg = stg == NST - 1 ? 0 : stg + 1;
-            stream_adj_row<EDGE, 5 % UNR>(k, w, r + 5, stg); stg = stg == NST - 1 ? 0 : stg + 1;
+        for (; kk < 4; kk += UNR) {
+            const int r = r0 + kk;
+            stream_adj_row<EDGE, 0, PBL>(k, w, r, stg); stg = stg == NST - 1 ? 0 : stg + 1;
+            if (UNR > 1) { stream_adj_row<EDGE, 1 % UNR, PBL>(k, w, r + 1, stg); stg = stg == NST - 1 ? 0 : stg + 1; }
+            win_shift<UNR>(w.sz); win_shift<UNR>(w.sx); win_shift<UNR>(w.sxz); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx);
         }
-        if (UNR < 6) { win_shift<UNR>(w.sz); win_shift<UNR>(w.sx); win_shift<UNR>(w.sxz); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); }
+    }
+#pragma unroll 1
+    for (; kk < niter; kk += UNR) {
+        const int r = r0 + kk;
+        stream_adj_row<EDGE, 0, PBM>(k, w, r, stg); stg = stg == NST - 1 ? 0 : stg + 1;
+        if (UNR > 1) { stream_adj_row<EDGE, 1 % UNR, PBM>(k, w, r + 1, stg); stg = stg == NST - 1 ? 0 : stg + 1; }
+        win_shift<UNR>(w.sz); win_shift<UNR>(w.sx); win_shift<UNR>(w.sxz); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx);
         if (EDGE) { w.qxx[0] = w.qxx[1]; w.qxx[1] = w.qxx[2]; w.qxz[0] = w.qxz[1]; w.qxz[1] = w.qxz[2]; }
     }
     cp_wait<0>();
@@ -1059,7 +1100,7 @@ __device__ __forceinline__ void stream_rec_issue(const RecCtx &k, const int r, c
     cp_commit();
 }
 
-template <bool EDGE, int U>
+template <bool EDGE, int U, int PB>
 __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const int r, const int stage)
 {
     const int ld = k.ld;
@@ -1126,7 +1167,7 @@ __device__ __forceinline__ void stream_rec_row(const RecCtx &k, RecWin &w, const
         for (int c = 0; c < 4; c++) w.ga_prev[c] = ga[c];
     }
     // ---- stage 2: stresses of time `it` at row q = r-2 ; lambda / mu imaging
-    {
+    if (PB == 0 || (PB == 2 && (r - 2 >= k.zc0 - 1) && (r - 2 < k.zc1))) {      // warp-uniform: owned rows, and the row above them for its shear term (sh_prev)
         const int q = r - 2;
         const float4 v0 = w.vz[u % 6], v1 = w.vz[(u + 1) % 6], v2 = w.vz[(u + 2) % 6], v3 = w.vz[(u + 3) % 6];
         const float4 u0 = w.vx[(u + 1) % 6], u1 = w.vx[(u + 2) % 6], u2 = w.vx[(u + 3) % 6], u3 = w.vx[(u + 4) % 6];
@@ -1240,19 +1281,29 @@ __device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs
     for (int j = 0; j < RC_NST - 1; j++) stream_rec_issue(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
     constexpr int UNR = EDGE ? 1 : SW_UNR_REC;
-    int stage = 0;
+    static_assert(UNR == 1 || UNR == 2, "one or two rows per trip");
+    // stage 2 is needed from row q = zc0 - 1 on (its shear term enters row zc0): two lead-in rows without it for interior warps
+#ifdef EXP_NO_LEADIN
+    constexpr int PBM = 0, PBL = 0;
+#else
+    constexpr int PBM = EDGE ? 2 : 0, PBL = EDGE ? 2 : 1;
+#endif
+    int stage = 0, kk = 0;
+    if (!EDGE) {
 #pragma unroll 1
-    for (int kk = 0; kk < niter; kk += UNR) {
-        const int r = r0 + kk;
-        stream_rec_row<EDGE, 0>(k, w, r, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
-        if (UNR > 1) { stream_rec_row<EDGE, 1 % UNR>(k, w, r + 1, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1; }
-        if (UNR > 2) { stream_rec_row<EDGE, 2 % UNR>(k, w, r + 2, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1; }
-        if (UNR > 3) {
-            stream_rec_row<EDGE, 3 % UNR>(k, w, r + 3, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
-            stream_rec_row<EDGE, 4 % UNR>(k, w, r + 4, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
-            stream_rec_row<EDGE, 5 % UNR>(k, w, r + 5, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
+        for (; kk < 2; kk += UNR) {
+            const int r = r0 + kk;
+            stream_rec_row<EDGE, 0, PBL>(k, w, r, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
+            if (UNR > 1) { stream_rec_row<EDGE, 1 % UNR, PBL>(k, w, r + 1, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1; }
+            win_shift<UNR>(w.szz); win_shift<UNR>(w.sxz); win_shift<UNR>(w.sxx); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx);
         }
-        if (UNR < 6) { win_shift<UNR>(w.szz); win_shift<UNR>(w.sxz); win_shift<UNR>(w.sxx); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx); }
+    }
+#pragma unroll 1
+    for (; kk < niter; kk += UNR) {
+        const int r = r0 + kk;
+        stream_rec_row<EDGE, 0, PBM>(k, w, r, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1;
+        if (UNR > 1) { stream_rec_row<EDGE, 1 % UNR, PBM>(k, w, r + 1, stage); stage = stage == RC_NST - 1 ? 0 : stage + 1; }
+        win_shift<UNR>(w.szz); win_shift<UNR>(w.sxz); win_shift<UNR>(w.sxx); win_shift<UNR>(w.vz); win_shift<UNR>(w.vx);
     }
     cp_wait<0>();
 }
@@ -1320,7 +1371,7 @@ __device__ __forceinline__ void stream_sp_issue(const SpCtx &k, const int r, con
     cp_commit();
 }
 
-template <int U>
+template <int U, int PB>
 __device__ __forceinline__ void stream_sp_row(const SpCtx &k, SpWin &w, const int r, const int stage)
 {
     const int ld = k.ld, nzA = k.nzA;
@@ -1361,7 +1412,7 @@ __device__ __forceinline__ void stream_sp_row(const SpCtx &k, SpWin &w, const in
         if (k.lown && rown) { const size_t ro = (size_t)r * ld; stq(k.o + F_VZ * fsz + ro, rvz); stq(k.o + F_VX * fsz + ro, rvx); }
     }
     // ---- phase B: stresses at row q = r-2 from the new velocities: vz rows q-2..q+1, vx rows q-1..q+2
-    {
+    if (PB == 0 || (PB == 2 && (r - 2 >= k.zc0) && (r - 2 < k.zc1))) {      // warp-uniform: nothing of this phase is kept for a row the chunk does not own
         const int q = r - 2;
         const float4 v0 = w.vz[u % 6], v1 = w.vz[(u + 1) % 6], v2 = w.vz[(u + 2) % 6], v3 = w.vz[(u + 3) % 6];
         const float4 u0 = w.vx[(u + 1) % 6], u1 = w.vx[(u + 2) % 6], u2 = w.vx[(u + 3) % 6], u3 = w.vx[(u + 4) % 6];
@@ -1473,11 +1524,17 @@ __global__ void __launch_bounds__(SW_NT, SW_MINB) k_stream_sponge(const KArgs a,
 #pragma unroll
     for (int j = 0; j < SP_NST - 1; j++) stream_sp_issue(k, r0 + j, j);
     const int niter = (k.zc1 - k.zc0) + 4;
-    int stg = 0;
+    int stg = 0, kk = 0;
 #pragma unroll 1
-    for (int kk = 0; kk < niter; kk += 2) {
-        stream_sp_row<0>(k, w, r0 + kk, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
-        stream_sp_row<1>(k, w, r0 + kk + 1, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
+    for (; kk < 4; kk += 2) {      // lead-in rows: velocities only (their stress row q = r - 2 is not owned)
+        stream_sp_row<0, 1>(k, w, r0 + kk, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
+        stream_sp_row<1, 1>(k, w, r0 + kk + 1, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
+        win_shift<2>(w.sz); win_shift<2>(w.sx); win_shift<2>(w.sxz); win_shift<2>(w.vz); win_shift<2>(w.vx);
+    }
+#pragma unroll 1
+    for (; kk < niter; kk += 2) {
+        stream_sp_row<0, 0>(k, w, r0 + kk, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
+        stream_sp_row<1, 0>(k, w, r0 + kk + 1, stg); stg = stg == SP_NST - 1 ? 0 : stg + 1;
         win_shift<2>(w.sz); win_shift<2>(w.sx); win_shift<2>(w.sxz); win_shift<2>(w.vz); win_shift<2>(w.vx);
     }
     cp_wait<0>();

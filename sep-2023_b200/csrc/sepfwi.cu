@@ -800,16 +800,12 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     if (!items_out && want && h->plan_sig[which] == want) { sa = h->plan_sa[which]; return 0; }
     memset(&sa, 0, sizeof(sa));
     const int model = which;
-    const double mult = 1.0;
     const int nStrips = (d.nx + SW_OWN - 1) / SW_OWN;
     // interior rows [zi0, zi1) / strips: the adjoint sweep keeps CPML memory on strips nPml + 2 wide (el_stress_adj.cu:67-72),
     // a warp recomputes a 2-cell halo, and the reverse sweep restores a ring that reaches 3 cells into the interior:
     // the branch-free variants need a margin of nPml + 5
     const int zi0 = d.nPml + 5, zi1 = d.nzA - d.nPml - 5;
-    const double conc = (double)h->nSM * h->warps_per_sm;
     auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 3 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 4; };
-    int nInnerStrips = 0;
-    for (int sx = 0; sx < nStrips; sx++) nInnerStrips += strip_inner(sx) ? 1 : 0;
     // Two regimes (round 2, calibrated with tools/sweep_plan.sh on the B200):
     //  * the batch's working set stays in the 126 MB L2 (one shot of the BASELINE grids, the reference's 19-shot experiment): the
     //    launch is one to two waves of latency-bound items -- a CPML row of the adjoint sweep takes ~2.5 us against 0.4 us for an
@@ -824,6 +820,8 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     if (bl < 0.5) {
         static const double rho_res[3] = {2.0, 3.0, 4.0};             // cost of an edge row in interior rows (latency regime)
         const double ci = 1.0 + 2.0 * bl, rho = rho_res[model] * (1.0 + 0.25 * bl), P = 3.0;      // P: prologue, in rows
+        static const double lead[3] = {2.2, 2.6, 2.2};                // cost of the four lead-in rows of an item, in full rows
+        const double H = lead[model];
         const int nslots = h->nSM * (h->warps_per_sm / SW_WPB);
         // (measured: below 8 interior / 2 edge rows per item the 4-row halo and the prologue only add work)
         static const int lzs[] = {8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128};
@@ -840,9 +838,10 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
                         int rows = a1 - a0;
                         if (model == 1) {      // reconstruction: rows outside interior + ring are skipped, items without any return at once
                             rows = std::max(0, std::min(a1, d.z1 + 3) - std::max(a0, d.nPml - 2));
-                            if (rows == 0) { cost.push_back(0.2f); continue; }
+                            if (rows == 0) continue;      // not launched (see below)
                         }
-                        cost.push_back(is_edge ? (float)((rows + 4 + P) * rho) : (float)((((rows + 4 + 1) / 2) * 2 + P) * ci));
+                        // the four lead-in rows run the first phase only (the second is skipped for rows the chunk does not own)
+                        cost.push_back(is_edge ? (float)((rows + H + P) * rho) : (float)((((rows + 4 + 1) / 2) * 2 - 4 + H + P) * ci));
                     }
                 };
                 for (int sx = 0; sx < nStrips; sx++) { piece(0, zi0, le, true); piece(zi1, d.nzA, le, true); }
@@ -866,32 +865,42 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
                 if (end < bestc - 1e-9) { bestc = end; best = Lz; Le = le; }
             }
     } else {
-    // wave model: whole waves of `conc` warps, each wave as long as its longest item.  Interior items run
-    // 2 ceil((Lz+4)/2) rows, edge items Le + 4 rows at edge_cost x the cost per row.
-    // measured cost of an edge row relative to an interior row: in throughput (many waves, HBM-bound) and in latency
-    // (a lone warp per scheduler: shorter look-ahead, register moves); the CPML rows of the adjoint sweep are the expensive ones
-    static const double edge_thr[3] = {1.15, 1.1, 1.8}, edge_lat[3] = {2.0, 1.6, 2.5};
-    const double edge_cost = edge_thr[model], edge_latc = edge_lat[model];
-    auto counts = [&](int Lz, int Le, double &n_in, double &n_ed) {
-        const int nch = (zi1 - zi0 + Lz - 1) / Lz, nche = (zi1 - zi0 + Le - 1) / Le, ntb = 2 * ((zi0 + Le - 1) / Le);
-        n_in = (double)nInnerStrips * nch;
-        n_ed = (double)(nStrips - nInnerStrips) * nche + (double)nStrips * ntb;
-    };
+    // HBM regime (calibrated on the 8000 x 2000 grid and on 8 - 64-shot batches of the C3 grid, tools/sweep_plan.sh): all resident
+    // warps share the memory bandwidth, so the launch takes (total row-work) / (warp slots) -- plus what a partly filled last wave
+    // loses: measured, a last wave filled to a fraction f of the CTA slots costs g(f) = min(1.5 f, 0.5 + 0.5 f) of a full one
+    // (f = 0.11: 0.10, 0.28: 0.51, 0.45: 0.69, 0.8: 0.85 on the reconstruction kernel), because the memory system is not
+    // saturated by few warps.  An edge row costs edge_thr interior rows in throughput and, as a lone
+    // item under a saturated memory system, edge_lat in latency (adjoint sweep: 37-row edge items took 290 us against 205 for 12).
+    static const double edge_thr[3] = {1.15, 1.1, 1.8}, edge_lat0[3] = {2.0, 1.6, 2.5}, edge_lat[3] = {2.5, 2.0, 5.0};
+    const int nslots = h->nSM * (h->warps_per_sm / SW_WPB);
     static const int les[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128};
-    for (int Lz = 2; Lz <= 128; Lz += 6)
+    auto pieces = [&](int z0, int z1, int L, bool xlive, double &n, double &rows_sum) {       // live items of one strip segment
+        const int np = (z1 - z0 + L - 1) / L;
+        for (int c = 0; c < np; c++) {
+            const int a0 = z0 + (int)((long long)(z1 - z0) * c / np), a1 = z0 + (int)((long long)(z1 - z0) * (c + 1) / np);
+            int rows = a1 - a0;
+            if (model == 1) { rows = xlive ? std::max(0, std::min(a1, d.z1 + 3) - std::max(a0, d.nPml - 2)) : 0; if (rows == 0) continue; }
+            n += 1.0; rows_sum += rows;
+        }
+    };
+    for (int Lz = 8; Lz <= 64; Lz += 2)       // (taller chunks measured worse: 98 rows +5 - 10 % on the 8000 x 2000 grid)
         for (int le : les) {
-            double n_in, n_ed;
-            counts(Lz, le, n_in, n_ed);
-            const double it_i = 6 * ((Lz + 4 + 5) / 6) + 3.0, it_e = (le + 4 + 3.0) * edge_cost;   // rows per item (+3: prologue)
-            const double work = (n_in * it_i + n_ed * it_e) * nb * mult / conc, longest = std::max(it_i, (le + 4 + 3.0) * edge_latc);
-            // one wave or less: the longest item is the time; many waves: throughput plus half an item of tail
-            double c = std::max(longest, work + 0.5 * longest);
-            // a few waves: whole waves of latency-bound items.  The reconstruction kernel's items outside
-            // the interior + ring return at once and do not occupy a slot.
-            const double live = model == 1 ? std::min(1.0, (double)(d.nzA - 2 * d.nPml + 4) / d.nzA) : 1.0;
-            const double waves = ceil((n_in + n_ed) * nb * mult * live / conc);
-            if (waves <= 3.0 && n_in + n_ed > 0)
-                c = std::max(c, waves * (n_in * it_i + n_ed * (le + 4 + 3.0) * edge_latc) / (n_in + n_ed));
+            double nE = 0, rE = 0, nI = 0, rI = 0;
+            for (int sx = 0; sx < nStrips; sx++) {
+                const int x0 = sx * SW_OWN;
+                const bool xlive = !(x0 + SW_OWN <= d.nPml - 2 || x0 > d.x1 + 2);
+                pieces(0, zi0, le, xlive, nE, rE); pieces(zi1, d.nzA, le, xlive, nE, rE);
+                if (strip_inner(sx)) pieces(zi0, zi1, Lz, xlive, nI, rI); else pieces(zi0, zi1, le, xlive, nE, rE);
+            }
+            if (nE + nI == 0) continue;
+            const double tI = 2 * ((Lz + 4 + 1) / 2) + 3.0, tE = le + 4 + 3.0;       // rows an item marches (+3: prologue)
+            const double work = (rE + nE * 7.0) * edge_thr[model] + (rI + nI * (tI - Lz));
+            const double ctas = ceil((nE + nI) / SW_WPB) * nb, wv = ctas / nslots, f = wv - floor(wv);
+            const double g = std::min(1.5 * f, 0.5 + 0.5 * f), tail_item = nI > 0 ? tI : tE * edge_thr[model];
+            // + half of the longest item: the items of the last shot(s) start late and finish unevenly
+            const double longest = std::max(nI > 0 ? tI : 0.0, tE * edge_lat0[model]);
+            double c = work * nb / ((double)nslots * SW_WPB) + (g - f) * tail_item + 0.5 * longest;
+            c = std::max(c, std::max(nI > 0 ? tI : 0.0, tE * edge_lat[model]));      // never shorter than its longest item
             if (c < bestc - 1e-9) { bestc = c; best = Lz; Le = le; }
         }
     }
@@ -927,6 +936,14 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     std::stable_sort(inner.begin(), inner.end(), [&](const int4 &p, const int4 &q) {
         const int hp = heavy[p.x / SW_OWN] ? 0 : 1, hq = heavy[q.x / SW_OWN] ? 0 : 1;
         return hp != hq ? hp < hq : p.y < q.y; });
+    if (which == 1) {
+        // the reverse sweep only touches interior + ring = [nPml-2, z1+2] x [nPml-2, x1+2]: items outside it would return at once but
+        // still hold a warp of their CTA until its other warps finish -- they are not launched at all
+        auto dead = [&](const int4 &w) {
+            return std::max(w.y, d.nPml - 2) >= std::min(w.z, d.z1 + 3) || w.x + SW_OWN <= d.nPml - 2 || w.x > d.x1 + 2;
+        };
+        edge.erase(std::remove_if(edge.begin(), edge.end(), dead), edge.end());
+    }
     edge.insert(edge.end(), inner.begin(), inner.end());
     if (items_out) { *items_out = edge; return 0; }      // host-only planning (sepfwi_plan_stream): nothing is uploaded
     if (edge.size() > h->work_cap[which]) {

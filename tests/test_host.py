@@ -271,7 +271,7 @@ def test_resident_planner_invariants_over_many_grids():
 
 def test_streaming_work_lists_tile_the_grid_exactly():
     """sepfwi_plan_stream (host arithmetic only): for random grids, CPML widths and batch sizes the work list of each streaming
-    kernel covers every (row, 120-column strip) of the live grid exactly once, interior (branch-free) items keep the nPml + 5 margin
+    kernel covers every (row, 120-column strip) of the live grid (the reverse sweep: of interior + ring) exactly once, interior (branch-free) items keep the nPml + 5 margin
     from every CPML strip, edge items come first, and no chunk is empty."""
     import ctypes as C
     from sepfwi import _lib
@@ -298,6 +298,12 @@ def test_streaming_work_lists_tile_the_grid_exactly():
                 cover[x0 // 120, z0:z1] += 1
                 if not edge:
                     assert z0 >= nPml + 5 and z1 <= nzA - nPml - 5 and x0 - 4 >= nPml + 3 and x0 + 123 <= nx - nPml - 4
-            assert np.all(cover == 1), (nz, nx, nPml, nb, which)
+            if which == 1:      # the reverse sweep: interior + 2-cell ring exactly once, nothing launched that lies wholly outside it
+                zl, zh, xl, xh = nPml - 2, nzA - nPml + 2, nPml - 2, nx - 1 - nPml + 2
+                live = np.array([x0 + 120 > xl and x0 <= xh for x0 in range(0, nstrips * 120, 120)])
+                assert np.all(cover[live, zl:zh] == 1) and np.all(cover <= 1), (nz, nx, nPml, nb, which)
+                assert np.all(np.minimum(it[:, 2], zh) > np.maximum(it[:, 1], zl)) and np.all(live[it[:, 0] // 120])
+            else:
+                assert np.all(cover == 1), (nz, nx, nPml, nb, which)
             first_inner = np.argmax(it[:, 3] == 0) if np.any(it[:, 3] == 0) else len(it)
             assert np.all(it[first_inner:, 3] == 0)                  # edge items first
