@@ -671,7 +671,10 @@ __device__ __forceinline__ void stream_adj_issue(const AdjCtx &k, const int r, c
     cp16(sb + AA_SZ * 512, k.g + F_SZZ * fsz + r2); cp16(sb + AA_SX * 512, k.g + F_SXX * fsz + r2); cp16(sb + AA_SXZ * 512, k.g + F_SXZ * fsz + r2);
     cp16(sb + AA_OVZ * 512, k.g + F_VZ * fsz + r0); cp16(sb + AA_OVX * 512, k.g + F_VX * fsz + r0);
     cp16(sb + AA_LAM * 512, k.m + M_LAM * fsz + r0); cp16(sb + AA_MU * 512, k.m + M_MU * fsz + r0); cp16(sb + AA_MUA * 512, k.m + M_MUAVE * fsz + r0);
-    cp16(sb + AA_BYA * 512, k.m + M_BYCA * fsz + rq); cp16(sb + AA_BYB * 512, k.m + M_BYCB * fsz + rq);
+    // buoyancies: interior warps need row r-2 (phase B); edge warps take row r for the CPML memory update of phase A -- phase B then
+    // re-reads row r-2 in line, an L1 hit (it was requested two iterations earlier), where row r in line was an L2 round trip per row
+    const size_t rb = EDGE ? r0 : rq;
+    cp16(sb + AA_BYA * 512, k.m + M_BYCA * fsz + rb); cp16(sb + AA_BYB * 512, k.m + M_BYCB * fsz + rb);
     cp_commit();
 }
 
@@ -734,13 +737,8 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             }
             if (zp) {
                 const float *pz0 = k.psrc + (size_t)P_VX_Z * fsz + ro, *pz1 = k.psrc + (size_t)P_VZ_Z * fsz + ro;
-#ifdef EXP_NO_AZ
-                const float4 t3 = k.xany ? ldq(pz0 + ld) : sb[AZ_PVXZ * 32], s3 = k.xany ? ldq(pz1 + 2 * ld) : sb[AZ_PVZZ * 32];
-                const float4 t0 = t3, t1 = t3, t2 = t3, s0 = s3, s1 = s3, s2 = s3;
-#else
                 const float4 t0 = ldq(pz0 - 2 * ld), t1 = ldq(pz0 - ld), t2 = ldq(pz0), t3 = k.xany ? ldq(pz0 + ld) : sb[AZ_PVXZ * 32];
                 const float4 s0 = ldq(pz1 - ld), s1 = ldq(pz1), s2 = ldq(pz1 + ld), s3 = k.xany ? ldq(pz1 + 2 * ld) : sb[AZ_PVZZ * 32];
-#endif
                 const float a0[4] = Q4(t0), a1[4] = Q4(t1), a2[4] = Q4(t2), a3[4] = Q4(t3), b0[4] = Q4(s0), b1[4] = Q4(s1), b2[4] = Q4(s2), b3[4] = Q4(s3);
 #pragma unroll
                 for (int c = 0; c < 4; c++) { dpx[c] += azh * -DZ4(a0[c], a1[c], a2[c], a3[c]); dpz[c] += az * -DZ4(b0[c], b1[c], b2[c], b3[c]); }
@@ -760,11 +758,7 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             // neighbouring warps that recompute the same halo cells write the same values.
             w.qxx[2] = zero4; w.qxz[2] = zero4;      // what phase B would read back from pdst two rows later (zero outside the x strips)
             if (xl || zp) {
-#ifdef EXP_NO_BAR
-                const float4 bar4 = sb[AA_BYA * 32], bbr4 = sb[AA_BYB * 32];
-#else
-                const float4 bar4 = ldq(k.m + M_BYCA * fsz + ro), bbr4 = ldq(k.m + M_BYCB * fsz + ro);
-#endif
+                const float4 bar4 = sb[AA_BYA * 32], bbr4 = sb[AA_BYB * 32];      // row r (edge ring)
                 const float bar[4] = Q4(bar4), bbr[4] = Q4(bbr4);
                 unsigned vm = k.amask;                               // columns with a complete window that are active
                 if (k.lane == 0) vm &= 0xcu;
@@ -797,6 +791,9 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
                             n1[c] = bzh * n1[c] + bar[c] * nvz[c] * dt;
                         }
                     stq_halo(k.pdst + (size_t)P_SXZ_Z * fsz + ro, n0, k.lane); stq_halo(k.pdst + (size_t)P_SZZ_Z * fsz + ro, n1, k.lane);
+                    // phase B reads these rows back over the next four iterations (z stencils of the new memory variables): start
+                    // the L1 fill now instead of at the first dependent load
+                    pf_l1(k.pdst + (size_t)P_SXZ_Z * fsz + ro); pf_l1(k.pdst + (size_t)P_SZZ_Z * fsz + ro);
                 }
             }
         }
@@ -815,11 +812,11 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
         const float vzm2[4] = Q4(v0), vzm1[4] = Q4(v1), vzc[4] = Q4(v2), vzp1[4] = Q4(v3);
         const float vxm1[4] = Q4(u0), vxc[4] = Q4(u1), vxp1[4] = Q4(u2), vxp2[4] = Q4(u3);
         const float ozz[4] = Q4(w.sz[u % 6]), oxx[4] = Q4(w.sx[u % 6]), oxz[4] = Q4(w.sxz[u % 6]);     // old stresses of row r-2 live in slot u
-        const float4 bya4 = sb[AA_BYA * 32], byb4 = sb[AA_BYB * 32];
+        const size_t ro = (size_t)q * ld;      // q is an owned row here
+        const float4 bya4 = EDGE ? ldq(k.m + M_BYCA * fsz + ro) : sb[AA_BYA * 32], byb4 = EDGE ? ldq(k.m + M_BYCB * fsz + ro) : sb[AA_BYB * 32];
         const float ba[4] = Q4(bya4), bb[4] = Q4(byb4);
         float nzz[4], nxz[4], nxx[4];
         const bool qown = (q >= k.zc0) && (q < k.zc1);
-        const size_t ro = (size_t)q * ld;
         if (!EDGE) {
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -852,12 +849,8 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             }
             if (zpq) {
                 const float *pz0 = k.pdst + (size_t)P_SXZ_Z * fsz + ro, *pz1 = k.pdst + (size_t)P_SZZ_Z * fsz + ro;
-#ifdef EXP_NO_BZ
-                const float4 t0 = w.vz[0], t1 = w.vz[1], t2 = w.vz[2], t3 = w.vz[3], s0 = w.vx[0], s1 = w.vx[1], s2 = w.vx[2], s3 = w.vx[3];
-#else
                 const float4 t0 = ldq_rw(pz0 - ld), t1 = ldq_rw(pz0), t2 = ldq_rw(pz0 + ld), t3 = ldq_rw(pz0 + 2 * ld);
                 const float4 s0 = ldq_rw(pz1 - 2 * ld), s1 = ldq_rw(pz1 - ld), s2 = ldq_rw(pz1), s3 = ldq_rw(pz1 + ld);
-#endif
                 const float a0[4] = Q4(t0), a1[4] = Q4(t1), a2[4] = Q4(t2), a3[4] = Q4(t3), b0[4] = Q4(s0), b1[4] = Q4(s1), b2[4] = Q4(s2), b3[4] = Q4(s3);
 #pragma unroll
                 for (int c = 0; c < 4; c++) { dxz[c] += az * -DZ4(a0[c], a1[c], a2[c], a3[c]); dzz[c] = azh * -DZ4(b0[c], b1[c], b2[c], b3[c]); }
@@ -875,20 +868,12 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
             }
             // CPML memory of the adjoint stresses: owner-only, strips nPml + 2 wide (el_stress_adj.cu:67-72,88-95)
             if ((xl2 || zst) && k.lown) {
-#ifdef EXP_NO_BM
-                const float4 l4 = sb[AA_LAM * 32], m4 = sb[AA_MU * 32], a4 = sb[AA_MUA * 32];
-#else
                 const float4 l4 = ldq(k.m + M_LAM * fsz + ro), m4 = ldq(k.m + M_MU * fsz + ro), a4 = ldq(k.m + M_MUAVE * fsz + ro);
-#endif
                 const float lq[4] = Q4(l4), mq[4] = Q4(m4), maq[4] = Q4(a4);
                 if (xl2) {
                     const float4 f0 = ldq_c(k.cxa + C_BH * ld), f1 = ldq_c(k.cxa + C_B * ld);
                     const float bxh[4] = Q4(f0), bx[4] = Q4(f1);
-#ifdef EXP_NO_BO
-                    const float4 o0 = w.vz[1], o1 = w.vx[1];
-#else
                     const float4 o0 = ldq(k.psrc + (size_t)P_VZ_X * fsz + ro), o1 = ldq(k.psrc + (size_t)P_VX_X * fsz + ro);
-#endif
                     float n0[4] = Q4(o0), n1[4] = Q4(o1);
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
@@ -901,11 +886,7 @@ __device__ __forceinline__ void stream_adj_row(const AdjCtx &k, AdjWin &w, const
                     stq(k.pdst + (size_t)P_VZ_X * fsz + ro, mk4(n0)); stq(k.pdst + (size_t)P_VX_X * fsz + ro, mk4(n1));
                 }
                 if (zst) {
-#ifdef EXP_NO_BO
-                    const float4 o0 = w.vz[2], o1 = w.vx[2];
-#else
                     const float4 o0 = ldq(k.psrc + (size_t)P_VX_Z * fsz + ro), o1 = ldq(k.psrc + (size_t)P_VZ_Z * fsz + ro);
-#endif
                     float n0[4] = Q4(o0), n1[4] = Q4(o1);
 #pragma unroll
                     for (int c = 0; c < 4; c++)
@@ -1283,11 +1264,7 @@ __device__ __forceinline__ void stream_rec_body(const KArgs &a, const StreamArgs
     constexpr int UNR = EDGE ? 1 : SW_UNR_REC;
     static_assert(UNR == 1 || UNR == 2, "one or two rows per trip");
     // stage 2 is needed from row q = zc0 - 1 on (its shear term enters row zc0): two lead-in rows without it for interior warps
-#ifdef EXP_NO_LEADIN
-    constexpr int PBM = 0, PBL = 0;
-#else
     constexpr int PBM = EDGE ? 2 : 0, PBL = EDGE ? 2 : 1;
-#endif
     int stage = 0, kk = 0;
     if (!EDGE) {
 #pragma unroll 1
