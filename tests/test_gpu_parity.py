@@ -502,6 +502,49 @@ def test_resident_forward_on_random_grids(seed):
             assert rel_l2(ga[k], gb[k]) < 1e-4, (seed, k, res[0][1])
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_streaming_kernels_beyond_l2_on_random_grids(seed):
+    """Batches whose working set exceeds the L2 take the planner's other regime (whole waves of taller chunks, edge items of the
+    reverse sweep outside interior + ring not launched): random grids / CPML widths / batch sizes, streaming kernels (forward included)
+    vs the unfused baseline kernels."""
+    _, Propagator, ShotSpec = _mods()
+    rng = np.random.default_rng(300 + seed)
+    nPml = int(rng.choice([16, 32]))
+    nzo, nxo = int(rng.integers(250, 420)), int(rng.integers(800, 1300))
+    NZ, NX, nPad = problems.pad_rule(nzo, nxo, nPml)
+    nb = int(np.ceil(2.0e6 / ((NZ - nPad) * NX))) + int(rng.integers(0, 3))      # >= 2 M cells in flight: 26 arrays x 4 B > 200 MB
+    nt = 60
+    vp = problems.layered_vp(nzo, nxo, 1800.0, 3600.0, 5, rng, nlens=8, lens_amp=0.1, sigma=(3, 12))
+    model = problems.lame_from_vp(problems.pad_model(vp, nPml, nPad))
+    start = problems.lame_from_vp(problems.pad_model(problems.smooth(vp, 5), nPml, nPad))
+    stf = problems.ricker(25.0, nt, 1.0e-3)
+    shots = []
+    for _ in range(nb):
+        nrec = int(rng.integers(4, 40))
+        zs, xs = int(rng.integers(2, nzo - 2)) + nPml, int(rng.integers(2, nxo - 2)) + nPml
+        zr = np.clip(zs + rng.integers(-22, 23, nrec), 1, NZ - nPad - 2)
+        xr = np.clip(xs + rng.integers(-22, 23, nrec), 1, NX - 2)
+        shots.append(ShotSpec(zs, xs, zr, xr, stf))
+    res = {}
+    for kern in (3, 1):
+        with Propagator(NZ, NX, nPml, nPad, nt, 10.0, 10.0, 1.0e-3, 25.0, max_batch=nb, max_nrec=40, with_adjoint=True, device=0,
+                        kernels=kern) as P:
+            P.set_model(*model)
+            fwd = P.forward(shots)
+            P.set_model(*start)
+            res[kern] = (fwd, P.gradient(shots, [f["ett"] for f in fwd]))
+    for k in range(nb):
+        for c in ("pr", "vx", "vz", "ett"):
+            ref = res[1][0][k][c]
+            if np.abs(ref).max() > 0:
+                assert rel_l2(res[3][0][k][c], ref) < 1e-5, (seed, NZ, NX, nPml, nb, k, c)
+    ga, gb = res[3][1], res[1][1]
+    assert abs(gb["misfit"]) > 0 and abs(ga["misfit"] - gb["misfit"]) <= 1e-5 * abs(gb["misfit"])
+    for k in ("glam", "gmu", "grho"):
+        assert np.abs(gb[k]).max() > 0 and rel_l2(ga[k], gb[k]) < 1e-4, (seed, k)
+    assert rel_l2(np.stack(ga["gstf"]), np.stack(gb["gstf"])) < 1e-4
+
+
 def test_cufd_dropin_reads_das_sensitivity(tmp_path):
     """The C drop-in (sepfwi_cufd) honours "das_sensitivity" in survey_file.json like the Python op: rows (1, 0, 0) reproduce
     the stock horizontal fiber bit-exactly, an oriented fiber equals the Python front-end on the same files."""

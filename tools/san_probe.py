@@ -24,6 +24,18 @@ for kern in (0, 3):
         g = P.gradient(shots, [f["ett"] for f in fwd])
         print("kernels", kern, "misfit %.6e" % g["misfit"], "resident launches", P.resident_launches, "launches", P.launches)
 
+# interior (branch-free) warps with their lead-in loops, several strips and chunks: the medium grid, streaming kernels
+pm = problems.medium()
+pm.nSteps = min(nsteps, 16)
+pm.stf = pm.stf[:, :pm.nSteps]
+with make_prop(Propagator, pm, max_batch=2, with_adjoint=True, kernels=3) as P:
+    P.set_model(*pm.true)
+    shots = cuda_shots(pm, ShotSpec)
+    fwd = P.forward(shots)
+    P.set_model(*pm.start)
+    g = P.gradient(shots, [f["ett"] for f in fwd])
+    print("medium grid, kernels 3: misfit %.6e" % g["misfit"], "launches", P.launches)
+
 # round 2: the data-side operators, the sponge-flavour streaming kernel and the TMA operand path under the sanitizer too
 from sepfwi import _lib
 nrec = len(prob.x_rec)
