@@ -6,10 +6,14 @@ commented (DAS_Waveform_Inversion/Ops/FWI/Src/libCUFD.cu:353-457); the operators
 Src/utilities.cu.  Each function below cites the lines it follows; `condition()` strings them together in the order of the
 commented call sites, applied to the DAS component (the only component that enters the objective, libCUFD.cu:427).
 
-parity unpinned: the reference never runs this chain (the call sites are comments and its `source_update_adj` reads an
-uninitialised `d_coef`), so there is nothing to execute against -- the oracle is pinned to the *formulas* by the
-self-checks in tests/test_oracle.py (band-pass of in-band / out-of-band sinusoids, cross-misfit value and gradient by finite
-differences, Wiener update recovering a known filter).
+Pinned by execution: oracle/ref_dataops_shim.cu (compiled into oracle/_ref/libcufd_ref.so with the reference's sources) runs the
+reference's own kernels in the order and with the launch configurations of the commented call sites; its outputs on seeded traces are
+committed as tests/golden/dataops_ref.npz (tests/golden/make_dataops_golden.py, run on the B200) and tests/test_oracle.py holds this
+file to them, next to self-checks of the formulas (band-pass of in-band / out-of-band sinusoids, cross-misfit value and gradient by
+finite differences, Wiener update recovering a known filter).  Two quirks of the reference are NOT restated (both are launch-grid
+slips, not intent): its padded scratch rows are zero-filled over the first nt columns only (utilities.cu:1133 -- the golden run
+parks zeroed blocks in the allocator so that the rest is zero too), and its band-pass / coefficient kernels are launched over
+ceil(nt / 32) * 32 columns, so the Nyquist bin nt of the 2 nt transform stays unfiltered when nt is a multiple of 32.
 """
 import numpy as np
 
@@ -133,6 +137,8 @@ def condition(obs, cal, src, dt, if_win=False, win_start=None, win_end=None, wei
     if if_win:                                                        # :353-363
         obs = window_traces(obs, dt, win_start, win_end, w, src_weight, win_ratio)
         cal = window_traces(cal, dt, win_start, win_end, w, src_weight, win_ratio)
+    else:                                                             # :363-367: end tapers of win_ratio x record length
+        obs, cal = window_simple(obs, dt, win_ratio), window_simple(cal, dt, win_ratio)
     if filt is not None:                                              # :370-373
         obs, cal = bp_filter(obs, dt, filt), bp_filter(cal, dt, filt)
     if if_cross_misfit:                                               # :376-384
@@ -155,4 +161,6 @@ def condition(obs, cal, src, dt, if_win=False, win_start=None, win_end=None, wei
         res = bp_filter(res, dt, filt)
     if if_win:                                                        # :450-457
         res = window_traces(res, dt, win_start, win_end, w, src_weight, win_ratio)
+    else:
+        res = window_simple(res, dt, win_ratio)
     return dict(res=res, misfit=J, cal=cal, src=src_new, obs=obs)

@@ -19,7 +19,8 @@ namespace sepfwi {
 constexpr int DF_NT = 128;        // threads per block of the transforms
 constexpr int DF_CHUNK = 1024;    // samples / bins staged in shared memory per pass
 
-// cuda_window with per-trace windows and weights (utilities.cu:790-842); grid (ceil(nt / 256), nrec)
+// cuda_window with per-trace windows and weights (utilities.cu:790-842) or, with win_start == nullptr, its window-less overload
+// (utilities.cu:844-884: end tapers of ratio x record length, no weights); grid (ceil(nt / 256), nrec)
 __global__ void __launch_bounds__(256) k_win_traces(float *data, const int nrec, const int nt, const float dt, const float *win_start,
                                                      const float *win_end, const float *weights, const float src_weight, const float ratio)
 {
@@ -27,17 +28,18 @@ __global__ void __launch_bounds__(256) k_win_traces(float *data, const int nrec,
     if (it >= nt || r >= nrec) return;
     const float PI = 3.14159265358979323846f;
     const float t = it * dt, t_max = nt * dt;
-    float t0 = win_start[r], t3 = win_end[r];
+    float t0 = win_start ? win_start[r] : 0.0f, t3 = win_start ? win_end[r] : t_max;
     t0 = fminf(fmaxf(t0, 0.0f), t_max); t3 = fminf(fmaxf(t3, 0.0f), t_max);
     const float offset = (t3 - t0) * ratio;
     if (offset <= 0.0f) return;                       // "Window error 1": the trace is left as it is (:815-819)
+    if (!win_start && 2.0f * offset >= t3 - t0) return;      // "Window error 2" (:859-862)
     const float t1 = t0 + offset, t2 = t3 - offset;
     float amp;
     if (t >= t0 && t < t1) amp = sinf(PI / 2.0f * (t - t0) / (t1 - t0));
     else if (t >= t1 && t < t2) amp = 1.0f;
     else if (t >= t2 && t < t3) amp = cosf(PI / 2.0f * (t - t2) / (t3 - t2));
     else amp = 0.0f;
-    data[(size_t)r * nt + it] *= amp * amp * weights[r] * src_weight;
+    data[(size_t)r * nt + it] *= win_start ? amp * amp * weights[r] * src_weight : amp * amp;
 }
 
 // Forward transform of zero-padded real traces at the contiguous bins k0 .. k0 + nb - 1 of the length-n2 DFT:

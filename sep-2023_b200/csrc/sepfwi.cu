@@ -1433,8 +1433,11 @@ static int run_conditioning(sepfwi_handle *h, int s, const sepfwi_shot &sh, cuda
     if (o.if_win) {                                                   // :353-363
         k_win_traces<<<gt, 256, 0, st>>>(obs, ntr, nt, h->p.dt, wst, wen, wwt, srcw, o.win_ratio);
         k_win_traces<<<gt, 256, 0, st>>>(cal, ntr, nt, h->p.dt, wst, wen, wwt, srcw, o.win_ratio);
-        h->launches += 2;
+    } else {                                                          // :363-367: without windows the records still get their end tapers
+        k_win_traces<<<gt, 256, 0, st>>>(obs, ntr, nt, h->p.dt, nullptr, nullptr, nullptr, 1.0f, o.win_ratio);
+        k_win_traces<<<gt, 256, 0, st>>>(cal, ntr, nt, h->p.dt, nullptr, nullptr, nullptr, 1.0f, o.win_ratio);
     }
+    h->launches += 2;
     if (o.if_filter) { band_pass(h, obs, ntr, st); band_pass(h, cal, ntr, st); }                    // :370-373
     if (o.if_cross_misfit) { k_normfacts<<<ntr, 256, 0, st>>>(obs, cal, nt, h->d_nf, ntr); h->launches++; }   // :376-384
     if (o.if_src_update) {                                            // :387-394, source_update utilities.cu:1170-1276
@@ -1470,7 +1473,9 @@ static int run_conditioning(sepfwi_handle *h, int s, const sepfwi_shot &sh, cuda
     }
     if (o.if_cross_misfit) { k_cross_adjoint<<<gt, 256, 0, st>>>(obs, cal, h->d_nf, ntr, nt, wwt, srcw, res); h->launches++; }   // :436-443
     if (o.if_filter) band_pass(h, res, ntr, st);                      // :446-448
-    if (o.if_win) { k_win_traces<<<gt, 256, 0, st>>>(res, ntr, nt, h->p.dt, wst, wen, wwt, srcw, o.win_ratio); h->launches++; }   // :450-457
+    if (o.if_win) k_win_traces<<<gt, 256, 0, st>>>(res, ntr, nt, h->p.dt, wst, wen, wwt, srcw, o.win_ratio);       // :450-457
+    else k_win_traces<<<gt, 256, 0, st>>>(res, ntr, nt, h->p.dt, nullptr, nullptr, nullptr, 1.0f, o.win_ratio);
+    h->launches++;
     CU(cudaGetLastError());
     return 0;
 }

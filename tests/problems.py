@@ -143,3 +143,39 @@ def reference_test(nSteps=1501, nshots=19):
     x_src = np.arange(10, 200, 10)[:nshots]
     return Problem("reftest", nz, nx, 32, 20.0, 20.0, 2.0e-3, nSteps, 10.0, vt, vs_,
                    np.full(len(x_src), 1), x_src, np.full(181, 95), np.arange(10, 191), 0)
+
+
+# ---- data-side operators (tests/golden/make_dataops_golden.py, tests/test_oracle.py, tests/test_gpu_dataops.py) ----------------
+DATAOPS_CASES = {
+    "plain": dict(),                                  # only the window-less end tapers of libCUFD.cu:363-367 + L2 residual
+    "win": dict(if_win=True),
+    "filt": dict(filter=True),
+    "cross": dict(if_cross_misfit=True),
+    "srcupd": dict(if_src_update=True),
+    "win_filt": dict(if_win=True, filter=True),
+    "win_filt_cross": dict(if_win=True, filter=True, if_cross_misfit=True),
+    "all_l2": dict(if_win=True, filter=True, if_src_update=True),
+}
+
+
+def dataops_traces(nrec, nt, dt, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(nt) * dt
+    out = np.zeros((nrec, nt))
+    for r in range(nrec):
+        for f in rng.uniform(4.0, 60.0, 5):
+            out[r] += rng.normal() * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28))
+        out[r] *= np.exp(-((t - 0.45 * nt * dt) / (0.2 * nt * dt)) ** 2) * 1e2
+    return out.astype(np.float32)
+
+
+def dataops_case(nrec=9, nt=301, dt=2.0e-3):
+    """Seeded inputs of the data-side golden vectors: two trace gathers, per-trace windows and weights, a tapered Ricker source."""
+    obs, cal = dataops_traces(nrec, nt, dt, 1), dataops_traces(nrec, nt, dt, 2)
+    cal = (0.6 * obs + 0.4 * cal).astype(np.float32)
+    ws = (np.linspace(0.05, 0.2, nrec) * nt * dt).astype(np.float32)
+    we = (np.linspace(0.7, 0.95, nrec) * nt * dt).astype(np.float32)
+    wt = np.linspace(0.5, 1.5, nrec).astype(np.float32)
+    src = ricker(12.0, nt, dt, amp=1.0).astype(np.float32)
+    return dict(obs=obs, cal=cal, src=src, dt=dt, win_start=ws, win_end=we, weights=wt, src_weight=0.75,
+                filt=np.array([8.0, 15.0, 30.0, 45.0], np.float32))

@@ -66,6 +66,40 @@ def test_condition_matches_oracle(mk, opts):
         assert rel_l2(got["src_updated"], ref["src"]) < 1e-3, rel_l2(got["src_updated"], ref["src"])
 
 
+@pytest.mark.parametrize("opts", OPTS + [dict(if_cross_misfit=True, if_src_update=True)])
+def test_condition_matches_the_live_reference_kernels(opts):
+    """sepfwi_condition vs the reference's OWN kernels run on this GPU (oracle/_ref/libcufd_ref.so through oracle/ref_dataops_shim.cu,
+    in the order of the commented call sites libCUFD.cu:353-457): adjoint source, conditioned synthetic, misfit, updated source.
+    fp32 direct transforms vs fp32 cuFFT: 1e-4 (source: 1e-3)."""
+    from oracle import ref_dataops as R
+    from oracle import oracle as O
+    from sepfwi.engine import Propagator, ShotSpec
+    if not R.available():
+        pytest.skip("oracle/_ref/libcufd_ref.so without the data-ops entry points (built from /root/reference by oracle/Makefile)")
+    prob = problems.small()
+    nrec, nt, dt = len(prob.x_rec), prob.nSteps, prob.dt
+    obs, cal = _random_traces(nrec, nt, dt, 11), _random_traces(nrec, nt, dt, 12)
+    cal = (0.6 * obs + 0.4 * cal).astype(np.float32)
+    ws, we, wt = _windows(nrec, nt, dt)
+    with make_prop(Propagator, prob, max_batch=1, with_adjoint=True) as P:
+        sh = cuda_shots(prob, ShotSpec, [0])[0]
+        kw = {}
+        if opts.get("if_win"):
+            sh.win_start, sh.win_end, sh.trace_weights, sh.src_weight = ws, we, wt, 0.75
+            kw = dict(win_start=ws, win_end=we, weights=wt, src_weight=0.75)
+        P.set_data_options(**opts)
+        got = P.condition(sh, obs, cal)
+    o = dict(opts)
+    filt = o.pop("filter", None)
+    ref = R.condition(obs, cal, O.stf_taper(prob.stf[0], dt), dt, filt=filt, **o, **kw)
+    assert np.abs(ref["res"]).max() > 0
+    assert rel_l2(got["res"], ref["res"]) < 1e-4, rel_l2(got["res"], ref["res"])
+    assert rel_l2(got["syn"], ref["cal"]) < 1e-4
+    assert abs(got["misfit"] - 0.5 * ref["misfit"]) <= 1e-4 * abs(0.5 * ref["misfit"])
+    if opts.get("if_src_update"):
+        assert rel_l2(got["src_updated"], ref["src"]) < 1e-3, rel_l2(got["src_updated"], ref["src"])
+
+
 @pytest.mark.parametrize("opts", [dict(if_win=True, filter=[6.0, 10.0, 25.0, 40.0]), dict(if_cross_misfit=True)])
 def test_gradient_with_data_options_uses_the_conditioned_adjoint_source(opts):
     """Wiring into sepfwi_gradient: with options on, misfit = the chain's misfit and the gradient = the plain-L2 gradient for
