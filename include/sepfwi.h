@@ -102,7 +102,9 @@ typedef struct sepfwi_shot {
 
 /* Data-side operators applied to observed and synthetic DAS traces between the forward and the reverse-time loop, in the order of
  * the (commented) call sites libCUFD.cu:353-457; the switches are those of para_file.json (Parameter.cpp:139-176).  All off (the
- * default, and the reference's live behaviour): residual = obs - syn, misfit = 0.5 sum residual^2. */
+ * default, and the reference's live behaviour): residual = obs - syn, misfit = 0.5 sum residual^2.  As soon as one switch is on the
+ * whole section runs as written there: with if_win off, observed data, synthetic data and the residual still get the window-less end
+ * tapers of win_ratio x record length (cuda_window utilities.cu:844-884, call sites libCUFD.cu:363-367, 454-457). */
 typedef struct sepfwi_data_options {
     int   if_win;           /* per-trace windows + trace weights + source weight, cuda_window utilities.cu:790-842 (needs win_start / win_end) */
     float win_ratio;        /* taper fraction of the window length; 0 = 0.005 (libCUFD.cu:63)                            */
