@@ -26,6 +26,7 @@ from .engine import Propagator, ShotSpec
 
 _PROPS = {}
 _OBS = {}
+_AUTOB = {}      # (propagator key, nrec, nshots) -> shots per launch: torch.cuda.mem_get_info costs ~50 ms, a third of a small evaluation
 _LOCK = threading.Lock()
 
 
@@ -35,6 +36,7 @@ def clear_cache():
             p.close()
         _PROPS.clear()
         _OBS.clear()
+        _AUTOB.clear()
     dist.clear_packed()
 
 
@@ -66,11 +68,17 @@ def auto_batch(nz, nx, nPad, nSteps, nrec, nPml, with_adjoint, nshots, device, p
 
 def _prop(para, device, with_adjoint, nrec, nshots):
     fiber = _lib.FIBER_EZZ if para.get("das_component", "exx") == "ezz" else _lib.FIBER_EXX
-    B = int(para.get("max_batch", 0)) or auto_batch(para["nz"], para["nx"], para["nPad"], para["nSteps"], nrec,
-                                                    para["nPoints_pml"], with_adjoint, nshots, device)
     race = bool(para.get("ref_race_compat", False))
     key = (device, para["nz"], para["nx"], para["nPoints_pml"], para["nPad"], para["nSteps"], float(para["dz"]),
            float(para["dx"]), float(para["dt"]), float(para["f0"]), fiber, bool(with_adjoint), race)
+    B = int(para.get("max_batch", 0))
+    if not B:
+        with _LOCK:
+            B = _AUTOB.get((key, nrec, nshots), 0)
+        if not B:
+            B = auto_batch(para["nz"], para["nx"], para["nPad"], para["nSteps"], nrec, para["nPoints_pml"], with_adjoint, nshots, device)
+            with _LOCK:
+                _AUTOB[(key, nrec, nshots)] = B
     with _LOCK:
         p = _PROPS.get(key)
         if p is not None and (p.params.max_nrec < nrec or p.params.max_batch < min(B, nshots)):
@@ -85,6 +93,8 @@ def _prop(para, device, with_adjoint, nrec, nshots):
                 if e.code != -5 or B <= 1:       # SEPFWI_ENOMEM: other tenants of the GPU; halve the batch and retry
                     raise
                 B = max(1, B // 2)
+                if not int(para.get("max_batch", 0)):
+                    _AUTOB[(key, nrec, nshots)] = B      # remember what fitted: the next call must not ask for the larger batch again
         _PROPS[key] = p
     return p
 
