@@ -5,7 +5,8 @@ forward run, the C3 single-shot gradient and the C4 vertical-fiber geometry, on 
 with nPml = 32, through the code paths the planner picks at those sizes (19 x 7 resident tiling, 15-strip streaming plan,
 reverse-time kernels, heavy injection strips).  The checker is the reference's OWN CUDA shot driver (`cufd`,
 DAS_Waveform_Inversion/Ops/FWI/Src/libCUFD.cu:32-820) compiled in place by oracle/Makefile and run live on the same GPU, and
--- for the vertical fiber, which the reference only supports through a source edit (libCUFD.cu:327-332) -- the CPU oracle.
+-- for the vertical fiber, which the reference only supports through a source edit (libCUFD.cu:327-332) -- the CPU oracle and the
+reference's driver compiled with that edit applied as two macro definitions (oracle/_ref/libcufd_ref_ezz.so).
 """
 import os
 
@@ -171,6 +172,47 @@ def test_c4_vertical_fiber_gradient_against_oracle():
     assert rel_l2(r["gmu"], gm) < 2e-4
     assert rel_l2(r["grho"], gd) < 2e-4
     assert rel_l2(np.stack(r["gstf"]), gs) < 2e-4
+
+
+def test_c4_vertical_fiber_gradient_against_live_reference(tmp_path):
+    """The same C4 geometry against the reference itself: oracle/_ref/libcufd_ref_ezz.so is the reference's shot driver with its two
+    call sites switched to recording_ezz / res_injection_ezz (macro definitions on the compile line of libCUFD.cu, oracle/Makefile --
+    the switch the reference makes by a source edit).  Channels every 2nd cell (165 of the 330): with adjacent channels the
+    reference's res_injection_ezz races at its 32-receiver block seams like res_injection_exx does (see the C3 test).  Two shots,
+    nt = 451, both in one batch on our side; traces 1e-4, misfit 1e-4, gradients 1e-3."""
+    from oracle import ref_cufd
+    from sepfwi.engine import Propagator, ShotSpec
+    if not ref_cufd.available(fiber=1):
+        pytest.skip("oracle/_ref/libcufd_ref_ezz.so not present (built by oracle/Makefile where /root/reference exists)")
+    nt = 451
+    w = _workload("c3", nt)
+    zrec = np.arange(10, 340, 2)
+    xrec = np.full(len(zrec), 850)
+    src = [(2, 20 + 26 * 31), (2, 20 + 26 * 33)]
+    stf = np.tile(w["stf"][None, :], (2, 1)).astype(np.float32)
+    ids = np.arange(2, dtype=np.int32)
+    para, data = _setup(tmp_path, w, [z for z, _ in src], [x for _, x in src], zrec, xrec, "ref_ezz")
+    ref_cufd.cufd(2, *w["true"], stf, ids, para, fiber=1)
+    obs = [np.fromfile(os.path.join(data, "Shot_ett%d.bin" % i), np.float32).reshape(len(zrec), nt) for i in range(2)]
+    Jr, gl, gm, gd, gs = ref_cufd.cufd(1, *w["start"], stf, ids, para, fiber=1)
+    assert Jr > 1.0 and np.abs(gl).max() > 0
+    P0 = w["nPml"]
+    with Propagator(w["nz"], w["nx"], w["nPml"], w["nPad"], nt, w["dz"], w["dx"], w["dt"], w["f0"], fiber=1, max_batch=2,
+                    max_nrec=len(zrec), with_adjoint=True, device=0) as P:
+        shots = [ShotSpec(zs + P0, xs + P0, zrec + P0, xrec + P0, stf[i]) for i, (zs, xs) in enumerate(src)]
+        P.set_model(*w["true"])
+        mine = P.forward(shots, comps=("ett",))
+        for i in range(2):
+            assert np.abs(obs[i]).max() > 1e-2
+            assert rel_l2(mine[i]["ett"], obs[i]) < TOL_REF_TRACE, i
+        P.set_model(*w["start"])
+        r = P.gradient(shots, obs)
+    assert abs(r["misfit"] - Jr) <= 1e-4 * abs(Jr)
+    assert rel_l2(r["glam"], gl) < TOL_REF_GRAD
+    assert rel_l2(r["gmu"], gm) < TOL_REF_GRAD
+    assert rel_l2(r["grho"], gd) < TOL_REF_GRAD
+    # the reference returns the stf gradient rows of the shots it processed at their local indices (libCUFD.cu:671-673)
+    assert rel_l2(np.stack(r["gstf"]), gs[:2]) < TOL_REF_GRAD
 
 
 def test_cufd_dropin_scratch_outputs_against_live_reference(tmp_path):

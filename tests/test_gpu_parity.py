@@ -223,7 +223,8 @@ def test_zero_residual_gives_zero_gradient():
         assert r["misfit"] == 0.0 and not np.any(r["glam"]) and not np.any(r["gmu"]) and not np.any(r["grho"])
 
 
-@pytest.mark.parametrize("mk,compat", [(problems.tiny, False), (problems.small, False), (problems.small_adj, True)])
+@pytest.mark.parametrize("mk,compat", [(problems.tiny, False), (problems.small, False), (problems.small_adj, True),
+                                       (lambda: problems.tiny(fiber=1), False)])
 def test_against_committed_reference_golden(golden_dir, mk, compat):
     """Golden vectors = outputs of the reference's own CUDA path (tests/golden/make_cufd_golden.py).
     small_adj: the reference's gradient contains its res_injection race (see problems.small); the product
