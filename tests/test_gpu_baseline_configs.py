@@ -88,6 +88,34 @@ def test_c2_full_forward_against_live_reference(tmp_path):
     _lib.lib().sepfwi_cufd_clear_cache()
 
 
+def test_c2_sponge_flavour_against_live_numba_reference():
+    """BASELINE configs[1] grid in the OTHER flavour: the reference's own Numba propagator (DAS_Waveform_Modeling/src/elasticSolver.py,
+    placed unmodified in oracle/_ref/numba_ref by oracle/Makefile) runs live on the host next to sepfwi.elasticSolver -- the
+    one-launch-per-step sponge kernel on the 1064 x 464 padded grid (nine strips, interior and rim items), 401 of the 4001 steps.
+    north_star: seismograms within 1e-4 relative L2, fp32 against the reference's fp64."""
+    from oracle import numba_ref
+    from sepfwi.elasticSolver import elasticSolver
+    if not numba_ref.available():
+        pytest.skip("oracle/_ref/numba_ref/elasticSolver.py or numba not present")
+    es = numba_ref.load()
+    w = _workload("c2")
+    nx, nz, nd, nt = 1000, 400, 32, 401
+    vp = np.ascontiguousarray(w["vp"].T, np.float64)                       # the Numba solver's arrays are (nx, nz)
+    vs, rho = vp / 1.732, 310.0 * vp ** 0.25
+    src = np.array([[5000.0, 20.0]])
+    xs = np.arange(4200.0, 5801.0, 50.0)
+    das = np.stack([xs, np.full(len(xs), 200.0)], 1)
+    geo = np.array([[4800.0, 100.0], [5300.0, 300.0]])
+    sens = np.tile(np.array([[1.0, 0, 0.3, 0, 0, 0.5]]), (len(xs), 1))     # exx, exz and ezz all enter the DAS channel
+    args = (nx, nz, nd, 10.0, 10.0, 1e-3, nt, 15.0, vp, vs, rho, src, das, geo, sens)
+    ref = es.elasticSolver(*args).forward_it(0, False)
+    mine = elasticSolver(*args).forward()[0]
+    for k in ("vx", "vz", "pr", "ett", "exx", "ezz", "exz"):
+        assert mine[k].shape == ref[k].shape
+        assert np.abs(ref[k]).max() > 0, k
+        assert rel_l2(mine[k], ref[k]) < TOL_REF_TRACE, (k, rel_l2(mine[k], ref[k]))
+
+
 @pytest.mark.parametrize("adjacent", [False, True])
 def test_c3_single_shot_gradient_against_live_reference(tmp_path, adjacent):
     """BASELINE configs[2], complete: Marmousi-like 1700 x 350 (padded 416 x 1764), nt = 4001, one shot, fiber at z = 2.
