@@ -283,6 +283,61 @@ def test_c5_grid_gradient_against_live_reference(tmp_path):
     assert rel_l2(r["gstf"][0], gs[0]) < TOL_REF_GRAD
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_small_grids_against_live_reference(tmp_path, seed):
+    """Random grid sizes (odd widths, heights that need different alignment pads), CPML widths 8 / 16 / 32, two to four shots with
+    random sources and scattered receivers (even columns only: no two receivers share an injection cell, so the reference's
+    residual injection is race-free): the reference's cufd run live vs ours through whatever plan these sizes get -- resident
+    forward tiling or streaming, several strips or one.  Traces 1e-4, misfit 1e-4, gradients 1e-3."""
+    from sepfwi.engine import Propagator, ShotSpec
+    ref_cufd = _ref()
+    rng = np.random.default_rng(900 + seed)
+    nPml = int(rng.choice([8, 16, 32]))
+    nzo, nxo = int(rng.integers(40, 150)), int(rng.integers(60, 330))
+    NZ, NX, nPad = problems.pad_rule(nzo, nxo, nPml)
+    nt, ns = 260, int(rng.integers(2, 5))
+    vp = problems.layered_vp(nzo, nxo, 1800.0, 3400.0, 4, rng, nlens=6, lens_amp=0.08, sigma=(2, 8))
+    true = problems.lame_from_vp(problems.pad_model(vp, nPml, nPad))
+    start = problems.lame_from_vp(problems.pad_model(problems.smooth(vp, 4), nPml, nPad))
+    w = dict(nz=NZ, nx=NX, nPml=nPml, nPad=nPad, nSteps=nt, dz=10.0, dx=10.0, dt=1.0e-3, f0=20.0)
+    stf1 = problems.ricker(20.0, nt, 1.0e-3)
+    stf = np.tile(stf1[None, :], (ns, 1)).astype(np.float32)
+    zs = [int(rng.integers(2, nzo - 2)) for _ in range(ns)]
+    xs = [int(rng.integers(2, nxo - 2)) for _ in range(ns)]
+    nrec = int(rng.integers(6, 30))
+    cells = set()
+    while len(cells) < nrec:
+        z, x = int(rng.integers(2, nzo - 2)), 2 * int(rng.integers(1, (nxo - 2) // 2))
+        # no receiver within 4 cells of a source: there the stf gradient -(szz + sxx) dt of the adjoint field is a difference of two
+        # large nearly opposite numbers and fp32 implementations differ among themselves by ~0.5 % (measured: reference vs our
+        # kernels vs the CPU oracle, seed 1 of this test with a receiver next to a source) -- conditioning, not semantics
+        if all(max(abs(z - a), abs(x - b)) > 4 for a, b in zip(zs, xs)):
+            cells.add((z, x))
+    zrec, xrec = (np.array(v) for v in zip(*sorted(cells)))
+    ids = np.arange(ns, dtype=np.int32)
+    para, data = _setup(tmp_path, w, zs, xs, zrec, xrec, "ref_rand%d" % seed)
+    ref_cufd.cufd(2, *true, stf, ids, para)
+    obs = [np.fromfile(os.path.join(data, "Shot_ett%d.bin" % i), np.float32).reshape(nrec, nt) for i in range(ns)]
+    ref_tr = {c: [np.fromfile(os.path.join(data, "Shot_%s%d.bin" % (c, i)), np.float32).reshape(nrec, nt) for i in range(ns)]
+              for c in ("pr", "vx", "vz")}
+    Jr, gl, gm, gd, gs = ref_cufd.cufd(1, *start, stf, ids, para)
+    assert Jr > 0 and np.abs(gl).max() > 0
+    with Propagator(NZ, NX, nPml, nPad, nt, 10.0, 10.0, 1.0e-3, 20.0, max_batch=ns, max_nrec=nrec, with_adjoint=True, device=0) as P:
+        shots = [ShotSpec(zs[i] + nPml, xs[i] + nPml, zrec + nPml, xrec + nPml, stf[i]) for i in range(ns)]
+        P.set_model(*true)
+        mine = P.forward(shots)
+        for i in range(ns):
+            assert rel_l2(mine[i]["ett"], obs[i]) < TOL_REF_TRACE, (seed, i)
+            for c in ("pr", "vx", "vz"):
+                assert rel_l2(mine[i][c], ref_tr[c][i]) < TOL_REF_TRACE, (seed, i, c)
+        P.set_model(*start)
+        r = P.gradient(shots, obs)
+    assert abs(r["misfit"] - Jr) <= 1e-4 * abs(Jr)
+    for mine_g, ref_g, name in ((r["glam"], gl, "glam"), (r["gmu"], gm, "gmu"), (r["grho"], gd, "grho")):
+        assert rel_l2(mine_g, ref_g) < TOL_REF_GRAD, (seed, name, NZ, NX, nPml, ns)
+    assert rel_l2(np.stack(r["gstf"]), gs[:ns]) < TOL_REF_GRAD
+
+
 def test_cufd_dropin_scratch_outputs_against_live_reference(tmp_path):
     """`scratch_dir_name` side channel (libCUFD.cu:731-751): Residual_Shot / Syn_Shot / CondObs_Shot{id}.bin -- the pressure residual
     (sample 0 zeroed), the synthetic pressure and the observed pressure as loaded -- written by sepfwi_cufd and by the reference's
