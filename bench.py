@@ -445,7 +445,8 @@ def headline_roofline(w, prof, peak, peak_src, rank, world, args):
     resident = "resident_fwd" in prof
     steps_per = {k: ((w["nSteps"] - 1) if k == "resident_fwd" else 1) for k in prof}
     alg = {"resident_fwd": B_FWD * w["live"] * (w["nSteps"] - 1), "stream_fwd": B_FWD * w["live"],
-           "stream_adj": B_ADJ * w["live"], "stream_recon": B_REC * w["interior"]}
+           "stream_adj": B_ADJ * w["live"], "stream_recon": B_REC * w["interior"],
+           "stream_bwd": B_ADJ * w["live"] + B_REC * w["interior"]}      # reconstruction + adjoint sweep in one launch
     kern = {k: {"avg_launch_us": 1e3 * avg(k), "launches_timed": prof[k][1], "algorithmic_bytes_per_launch": alg[k],
                 "achieved_GBs": alg[k] / (avg(k) * 1e-3) / 1e9, "frac": alg[k] / (avg(k) * 1e-3) / 1e9 / peak}
             for k in prof if k in alg and avg(k) > 0}
@@ -468,7 +469,7 @@ def headline_roofline(w, prof, peak, peak_src, rank, world, args):
                      "the HBM-bound figures are in `large` and `fwi`")}
     if is_grad:
         t_step = sum(step_us.values()) * 1e-6
-        a_all = (B_FWD * w["live"] + B_ADJ * w["live"] + B_REC * w["interior"]) / t_step / 1e9
+        a_all = (B_FWD * w["live"] + B_ADJ * w["live"] + B_REC * w["interior"]) / t_step / 1e9      # each byte count once: stream_bwd = recon + adj
         roof["whole_gradient_step"] = {"us": t_step * 1e6, "algorithmic_GBs": a_all, "frac": a_all / peak}
     if resident:
         roof["time_steps_per_launch"] = w["nSteps"] - 1
@@ -676,7 +677,8 @@ def extra_reference_experiment(ctx, peak):
 
 def _kernel_roofline(w, prof, peak, traffic):
     us = {k: 1e3 * ms / n for k, (ms, n) in prof.items()}
-    alg = {"stream_fwd": B_FWD * w["live"], "stream_adj": B_ADJ * w["live"], "stream_recon": B_REC * w["interior"]}
+    alg = {"stream_fwd": B_FWD * w["live"], "stream_adj": B_ADJ * w["live"], "stream_recon": B_REC * w["interior"],
+           "stream_bwd": B_ADJ * w["live"] + B_REC * w["interior"]}
     per = {}
     for k in us:
         if k in alg:
@@ -706,7 +708,7 @@ def extra_large(ctx, peak):
     traffic, tsrc = measured_traffic("c5s", 24, 1, ctx["rank"], ctx["world"], ctx["args"].no_ncu)
     us, per = _kernel_roofline(w, prof, peak, traffic)
     fk = [k for k in ("stream_fwd",) if k in us]
-    bk = [k for k in ("stream_recon", "stream_adj") if k in us]
+    bk = [k for k in ("stream_recon", "stream_adj", "stream_bwd") if k in us]
     tf, tb = sum(us[k] for k in fk) * 1e-6, sum(us[k] for k in bk) * 1e-6
     af = B_FWD * w["live"] / tf / 1e9
     ab = (B_ADJ * w["live"] + B_REC * w["interior"]) / tb / 1e9

@@ -198,7 +198,7 @@ long long sepfwi_bytes_per_slot(const sepfwi_params *p);
  * accumulated milliseconds and launch counts per kernel kind since the last sepfwi_set_profile. */
 enum { SEPFWI_K_RING_SAVE = 0, SEPFWI_K_STRESS_FWD, SEPFWI_K_VELOCITY_FWD, SEPFWI_K_RECORD, SEPFWI_K_VELOCITY_BWD,
        SEPFWI_K_STRESS_BWD, SEPFWI_K_VELOCITY_ADJ, SEPFWI_K_INJECT, SEPFWI_K_STRESS_ADJ, SEPFWI_K_STREAM_FWD, SEPFWI_K_STREAM_RECON,
-       SEPFWI_K_STREAM_ADJ, SEPFWI_K_RESIDENT_FWD, SEPFWI_NKERNEL };
+       SEPFWI_K_STREAM_ADJ, SEPFWI_K_RESIDENT_FWD, SEPFWI_K_STREAM_BWD /* reconstruction + adjoint sweep in one launch */, SEPFWI_NKERNEL };
 int sepfwi_set_profile(sepfwi_handle *h, int nsteps);
 int sepfwi_get_profile(sepfwi_handle *h, double *ms /*[SEPFWI_NKERNEL]*/, long long *count /*[SEPFWI_NKERNEL]*/);
 const char *sepfwi_kernel_name(int kind);

@@ -1306,6 +1306,46 @@ __global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_recon(const KArgs a, 
 #endif
 }
 
+// EXPERIMENT (SEPFWI_MERGE=1): the reverse-time step as ONE launch -- reconstruction and adjoint sweep of a step only read the
+// adjoint buffer `pa` and write disjoint arrays, so their CTAs can share a grid: the adjoint CTAs (slower items) come first.
+__global__ void __launch_bounds__(SW_NT, RC_MINB) k_stream_bwd(const KArgs a, const StreamArgs sr, const StreamArgs sa, const int nAdjCta)
+{
+    __shared__ __align__(16) float stage[SW_WPB][256];
+    extern __shared__ __align__(128) float smem[];
+    pdl_launch_dependents();
+    const int s = blockIdx.y;
+    const Dims &d = a.d;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if ((int)blockIdx.x < nAdjCta) {
+        if (blockIdx.x == 0) {
+            pdl_wait();
+            if (threadIdx.x == 0) {
+                const float *src = slot_state(a, s) + (size_t)(sa.pa ? S_ADJ1 : S_ADJ) * d.fsz;
+                const size_t i = (size_t)a.t.zs[s] * d.ldx + a.t.xs[s];
+                a.gstf[(size_t)s * d.nSteps + sa.it] = -(src[(size_t)F_SZZ * d.fsz + i] + a.t.rxz[s] * src[(size_t)F_SXX * d.fsz + i]) * d.dt;
+            }
+            return;
+        }
+        const int wg = ((int)blockIdx.x - 1) * SW_WPB + wp;
+        if (wg >= sa.nWork) return;
+        const int4 wk = __ldg(sa.work + wg);
+        const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + wp * AR_WARP_BYTES;
+        const float4 *sp = reinterpret_cast<const float4 *>(smem) + wp * (AR_WARP_BYTES / 16);
+        pdl_wait();
+        if (wk.w == 0) stream_adj_body<false>(a, sa, s, wk, lane, stage[wp], sw, sp);
+        else stream_adj_body<true>(a, sa, s, wk, lane, stage[wp], sw, sp);
+    } else {
+        const int wg = ((int)blockIdx.x - nAdjCta) * SW_WPB + wp;
+        if (wg >= sr.nWork) return;
+        const int4 wk = __ldg(sr.work + wg);
+        pdl_wait();
+        const unsigned sw = (unsigned)__cvta_generic_to_shared(smem) + wp * RC_WARP_BYTES;
+        const float4 *sp = reinterpret_cast<const float4 *>(smem) + wp * (RC_WARP_BYTES / 16);
+        if (wk.w == 0) stream_rec_body<false>(a, sr, s, wk, lane, sw, sp);
+        else stream_rec_body<true>(a, sr, s, wk, lane, sw, sp);
+    }
+}
+
 // ================================================================================================
 // Sponge flavour (DAS_Waveform_Modeling/src/elasticSolver.py:241-276, the Numba CPU propagator's scheme) as ONE launch per time step:
 //   phase A (row r)    v  = damp (v + D(sigma) b dt)            update_velocity :310-345 + the sponge :247-248

@@ -75,6 +75,8 @@ struct sepfwi_handle {
     // SEPFWI_LZ / SEPFWI_LZE chunk heights, SEPFWI_FORCE 1/2 force the interior / edge code path (timing only),
     // SEPFWI_PLAN_DEBUG prints the plans, SEPFWI_RES_DEBUG the resident kernel's timing switches
     int tune_lz = 0, tune_lze = 0, tune_force = 0, res_dbg = 0, res_forced_rpt = 0;
+    int pair_lz[3] = {0, 0, 0}, pair_le[3] = {0, 0, 0};      // chunk heights chosen jointly for the merged reverse-time launch (0: none)
+    int tune_merge = -1;   // SEPFWI_MERGE: reconstruction + adjoint sweep of a time step in one launch: -1 where it pays (stream_plan_pair), 0 never, 1 always
     int smem_pad = 0;      // SEPFWI_SMEM_PAD: extra dynamic shared memory per streaming CTA (experiment: shrinks the L1 carve-out)
     bool plan_debug = false, res_fake_refuse = false;
     bool res_attr_done[16] = {false};      // cudaFuncSetAttribute issued for k_resident_fwd<RPT> on this handle's device
@@ -125,7 +127,7 @@ struct sepfwi_handle {
 };
 
 static const char *k_names[SEPFWI_NKERNEL] = {"ring_save", "stress_fwd", "velocity_fwd", "record", "velocity_bwd",
-                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "stream_fwd", "stream_recon", "stream_adj", "resident_fwd"};
+                                              "stress_bwd", "velocity_adj", "inject", "stress_adj", "stream_fwd", "stream_recon", "stream_adj", "resident_fwd", "stream_bwd"};
 
 // Launch with programmatic stream serialization (the kernels call griddepcontrol.launch_dependents / .wait themselves).
 template <typename... KA, typename... A>
@@ -433,6 +435,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
     if (const char *e = getenv("SEPFWI_LZE")) h->tune_lze = atoi(e);
     if (const char *e = getenv("SEPFWI_FORCE")) h->tune_force = atoi(e);
     if (const char *e = getenv("SEPFWI_SMEM_PAD")) h->smem_pad = atoi(e);
+    if (const char *e = getenv("SEPFWI_MERGE")) h->tune_merge = atoi(e);
     if (const char *e = getenv("SEPFWI_RES_DEBUG")) h->res_dbg = atoi(e);
     if (const char *e = getenv("SEPFWI_RESIDENT_RPT")) h->res_forced_rpt = atoi(e);
     h->plan_debug = getenv("SEPFWI_PLAN_DEBUG") != nullptr;
@@ -449,6 +452,7 @@ extern "C" int sepfwi_create(const sepfwi_params *pp, int device, sepfwi_handle 
         CU(cudaFuncSetAttribute(k_stream_recon, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM + h->smem_pad));
         CU(cudaFuncSetAttribute(k_stream_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM + h->smem_pad));
         CU(cudaFuncSetAttribute(k_stream_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AR_SMEM + h->smem_pad));
+        CU(cudaFuncSetAttribute(k_stream_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RC_SMEM));
     }
     h->resident = h->stream && pp->kernels == 0 && d.nPml <= RS_PW;
     if (const char *e = getenv("SEPFWI_RESIDENT")) h->resident = h->resident && atoi(e) != 0;
@@ -786,6 +790,62 @@ static int max_nrec(int nb, const sepfwi_shot *shots)
     return m;
 }
 
+// Latency-regime cost of the CTAs of ONE shot for chunk heights (Lz interior, le edge), in interior-row units, launch order
+// (edge items first): an edge row costs rho interior rows, an item pays its lead-in rows and a prologue (calibrated on the B200
+// with forced-height sweeps, tools/sweep_plan.sh).  model: 0 forward, 1 reconstruction, 2 adjoint.
+static void l2_cta_costs(const sepfwi_handle *h, int nb, int model, int Lz, int le, std::vector<float> &cta)
+{
+    const Dims &d = h->d;
+    static const double narr[3] = {20.0, 26.0, 20.0};
+    const double ws = (double)nb * d.nzA * d.nx * 4.0 * narr[model];
+    const double bl = std::min(1.0, std::max(0.0, (ws - 60.0e6) / 140.0e6));
+    static const double rho_res[3] = {2.0, 3.0, 4.0}, lead[3] = {2.2, 2.6, 2.2};
+    const double ci = 1.0 + 2.0 * bl, rho = rho_res[model] * (1.0 + 0.25 * bl), P = 3.0, H = lead[model];
+    const int nStrips = (d.nx + SW_OWN - 1) / SW_OWN, zi0 = d.nPml + 5, zi1 = d.nzA - d.nPml - 5;
+    auto strip_inner = [&](int sx) { const int x0 = sx * SW_OWN; return x0 - 4 >= d.nPml + 3 && x0 + SW_OWN + 3 <= d.nx - d.nPml - 4; };
+    std::vector<float> cost;
+    auto piece = [&](int z0, int z1, int L, bool is_edge) {
+        const int n = (z1 - z0 + L - 1) / L;
+        for (int c = 0; c < n; c++) {
+            const int a0 = z0 + (int)((long long)(z1 - z0) * c / n), a1 = z0 + (int)((long long)(z1 - z0) * (c + 1) / n);
+            int rows = a1 - a0;
+            if (model == 1) {      // reconstruction: rows outside interior + ring are skipped, items without any are not launched
+                rows = std::max(0, std::min(a1, d.z1 + 3) - std::max(a0, d.nPml - 2));
+                if (rows == 0) continue;
+            }
+            cost.push_back(is_edge ? (float)((rows + H + P) * rho) : (float)((((rows + 4 + 1) / 2) * 2 - 4 + H + P) * ci));
+        }
+    };
+    for (int sx = 0; sx < nStrips; sx++) { piece(0, zi0, le, true); piece(zi1, d.nzA, le, true); }
+    for (int sx = 0; sx < nStrips; sx++) if (!strip_inner(sx)) piece(zi0, zi1, le, true);
+    for (int sx = 0; sx < nStrips; sx++) if (strip_inner(sx)) piece(zi0, zi1, Lz, false);
+    cta.clear();
+    for (size_t i = 0; i < cost.size(); i += SW_WPB) {
+        float dmax = 0.f;
+        for (size_t j = i; j < std::min(cost.size(), i + SW_WPB); j++) dmax = std::max(dmax, cost[j]);
+        cta.push_back(dmax);
+    }
+}
+
+// makespan of CTAs dispatched in order onto `nslots` slots (every CTA goes to the slot that frees first)
+static double list_schedule(const std::vector<const std::vector<float> *> &per_shot, int nb, int nslots, std::vector<double> &slot)
+{
+    slot.assign(nslots, 0.0);
+    auto cmp = [](double x, double y) { return x > y; };
+    std::make_heap(slot.begin(), slot.end(), cmp);
+    double end = 0.0;
+    for (int b = 0; b < nb; b++)
+        for (const std::vector<float> *v : per_shot)
+            for (float c : *v) {
+                std::pop_heap(slot.begin(), slot.end(), cmp);
+                const double t = slot.back() + c;
+                slot.back() = t;
+                std::push_heap(slot.begin(), slot.end(), cmp);
+                end = std::max(end, t);
+            }
+    return end;
+}
+
 // Work list of the streaming kernels: 120-column strips x row chunks, one warp each.
 //   * rows [0, nPml+2) and [nzA-nPml-2, nzA) and the strips that touch the x CPML / rim are "edge" items (slower per row:
 //     CPML memory variables, no look-ahead): they get shorter chunks and are listed first so they never form the tail;
@@ -818,50 +878,16 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     int best = 8, Le = 8;
     double bestc = 1e300;
     if (bl < 0.5) {
-        static const double rho_res[3] = {2.0, 3.0, 4.0};             // cost of an edge row in interior rows (latency regime)
-        const double ci = 1.0 + 2.0 * bl, rho = rho_res[model] * (1.0 + 0.25 * bl), P = 3.0;      // P: prologue, in rows
-        static const double lead[3] = {2.2, 2.6, 2.2};                // cost of the four lead-in rows of an item, in full rows
-        const double H = lead[model];
         const int nslots = h->nSM * (h->warps_per_sm / SW_WPB);
         // (measured: below 8 interior / 2 edge rows per item the 4-row halo and the prologue only add work)
         static const int lzs[] = {8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128};
         static const int les2[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
-        std::vector<float> cost;
-        std::vector<double> slot(nslots);
+        std::vector<float> cta;
+        std::vector<double> slot;
         for (int Lz : lzs)
             for (int le : les2) {
-                cost.clear();
-                auto piece = [&](int z0, int z1, int L, bool is_edge) {
-                    const int n = (z1 - z0 + L - 1) / L;
-                    for (int c = 0; c < n; c++) {
-                        const int a0 = z0 + (int)((long long)(z1 - z0) * c / n), a1 = z0 + (int)((long long)(z1 - z0) * (c + 1) / n);
-                        int rows = a1 - a0;
-                        if (model == 1) {      // reconstruction: rows outside interior + ring are skipped, items without any return at once
-                            rows = std::max(0, std::min(a1, d.z1 + 3) - std::max(a0, d.nPml - 2));
-                            if (rows == 0) continue;      // not launched (see below)
-                        }
-                        // the four lead-in rows run the first phase only (the second is skipped for rows the chunk does not own)
-                        cost.push_back(is_edge ? (float)((rows + H + P) * rho) : (float)((((rows + 4 + 1) / 2) * 2 - 4 + H + P) * ci));
-                    }
-                };
-                for (int sx = 0; sx < nStrips; sx++) { piece(0, zi0, le, true); piece(zi1, d.nzA, le, true); }
-                for (int sx = 0; sx < nStrips; sx++) if (!strip_inner(sx)) piece(zi0, zi1, le, true);
-                for (int sx = 0; sx < nStrips; sx++) if (strip_inner(sx)) piece(zi0, zi1, Lz, false);
-                // list scheduling: every CTA goes to the slot that frees first (min-heap of finish times)
-                std::fill(slot.begin(), slot.end(), 0.0);
-                double end = 0.0;
-                auto cmp = [](double x, double y) { return x > y; };
-                std::make_heap(slot.begin(), slot.end(), cmp);
-                for (int b = 0; b < nb; b++)
-                    for (size_t i = 0; i < cost.size(); i += SW_WPB) {
-                        float dmax = 0.f;
-                        for (size_t j = i; j < std::min(cost.size(), i + SW_WPB); j++) dmax = std::max(dmax, cost[j]);
-                        std::pop_heap(slot.begin(), slot.end(), cmp);
-                        const double t = slot.back() + dmax;
-                        slot.back() = t;
-                        std::push_heap(slot.begin(), slot.end(), cmp);
-                        end = std::max(end, t);
-                    }
+                l2_cta_costs(h, nb, model, Lz, le, cta);
+                const double end = list_schedule({&cta}, nb, nslots, slot);
                 if (end < bestc - 1e-9) { bestc = end; best = Lz; Le = le; }
             }
     } else {
@@ -904,6 +930,7 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
             if (c < bestc - 1e-9) { bestc = c; best = Lz; Le = le; }
         }
     }
+    if (h->pair_lz[which] >= 1) { best = h->pair_lz[which]; Le = h->pair_le[which]; }      // chosen jointly (stream_plan_pair)
     if (h->tune_lz >= 1) best = h->tune_lz;
     if (h->tune_lze >= 1) Le = h->tune_lze;
     sa.force = h->tune_force;
@@ -964,6 +991,53 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
     return 0;
 }
 
+
+// Work lists of the reverse-time step (adjoint sweep `sa`, reconstruction `sr`) and the decision whether both go into ONE launch
+// (k_stream_bwd: the two sweeps of a step only read the adjoint buffer and write disjoint arrays).  Measured on the B200: one launch
+// saves the inter-launch gap and lets the CTAs of one sweep fill the slots the other leaves idle in its last wave -- C3 single shot
+// 54 -> 41 us per step, 19-shot reference experiment 90 -> 80, 8 shots 230 -> 211, 8000 x 2000 503 -> 485 -- but with many waves per
+// launch (64 shots: 1450 -> 1565 us) the adjoint CTAs only lose: the merged launch needs the reconstruction kernel's 108 KB of
+// shared memory per CTA, which leaves them a quarter of their L1.  In the latency regime the chunk heights of both sweeps are
+// chosen together: makespan of the merged grid (per shot: adjoint CTAs, then reconstruction CTAs) by list scheduling.
+static int stream_plan_pair(sepfwi_handle *h, int nb, StreamArgs &sa, StreamArgs &sr, bool &merged, cudaStream_t st)
+{
+    const Dims &d = h->d;
+    const uint64_t want = h->staged_sig ? (h->staged_sig ^ ((uint64_t)nb << 48)) | 1ull : 0;
+    const bool cached = want && h->plan_sig[1] == want && h->plan_sig[2] == want;
+    const int nslots = h->nSM * (h->warps_per_sm / SW_WPB);
+    h->pair_lz[1] = h->pair_lz[2] = 0;
+    if (!cached) {
+        const double cells = (double)nb * d.nzA * d.nx * 4.0;
+        const bool l2 = (cells * 26.0 - 60.0e6) / 140.0e6 < 0.5;      // both sweeps in the latency regime (see stream_plan)
+        if (l2 && h->tune_merge != 0 && h->tune_lz < 1 && h->tune_lze < 1) {
+            static const int lzs[] = {8, 12, 16, 20, 24, 32, 48, 64}, les[] = {2, 3, 4, 6, 8, 12, 16};
+            constexpr int NL = 8, NE = 7;
+            std::vector<std::vector<float>> ca(NL * NE), cr(NL * NE);
+            for (int i = 0; i < NL; i++)
+                for (int j = 0; j < NE; j++) { l2_cta_costs(h, nb, 2, lzs[i], les[j], ca[i * NE + j]); l2_cta_costs(h, nb, 1, lzs[i], les[j], cr[i * NE + j]); }
+            for (auto &v : ca) v.insert(v.begin(), 0.05f);      // the CTA that writes the stf gradient
+            std::vector<double> slot;
+            double bestc = 1e300;
+            int ba = 0, br = 0;
+            for (int x = 0; x < NL * NE; x++)
+                for (int y = 0; y < NL * NE; y++) {
+                    // candidates with the same interior height but no interior items are duplicates: skipped by their equal cost vectors
+                    const double e = list_schedule({&ca[x], &cr[y]}, nb, nslots, slot);
+                    if (e < bestc - 1e-9) { bestc = e; ba = x; br = y; }
+                }
+            h->pair_lz[2] = lzs[ba / NE]; h->pair_le[2] = les[ba % NE];
+            h->pair_lz[1] = lzs[br / NE]; h->pair_le[1] = les[br % NE];
+            if (h->plan_debug) fprintf(stderr, "stream_plan_pair: nb %d adjoint Lz %d Le %d, reconstruction Lz %d Le %d, makespan %.1f\n", nb, h->pair_lz[2], h->pair_le[2], h->pair_lz[1], h->pair_le[1], bestc);
+        }
+    }
+    int rc = stream_plan(h, nb, 2, sa, st);
+    if (!rc) rc = stream_plan(h, nb, 1, sr, st);
+    h->pair_lz[1] = h->pair_lz[2] = 0;
+    if (rc) return rc;
+    const double waves = (double)nb * (1 + (sa.nWork + SW_WPB - 1) / SW_WPB + (sr.nWork + SW_WPB - 1) / SW_WPB) / nslots;
+    merged = h->tune_merge < 0 ? waves <= 6.5 : h->tune_merge != 0;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // Shared-memory-resident forward loop (kernels_resident.cuh): tiling plan, tables, cooperative launch.
@@ -1529,10 +1603,9 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
     dim3 rgrd((rx + BX - 1) / BX, (rz + BY - 1) / BY, nb);
     dim3 igrd((minj + 127) / 128, nb);
     StreamArgs sa, sr;
+    bool merged = false;
     if (h->stream) {
-        int rc = stream_plan(h, nb, 2, sa, st);
-        if (rc) return rc;
-        rc = stream_plan(h, nb, 1, sr, st);
+        int rc = stream_plan_pair(h, nb, sa, sr, merged, st);
         if (rc) return rc;
     }
     CU(cudaEventRecord(h->ev[2], st));
@@ -1542,6 +1615,14 @@ static int run_backward(sepfwi_handle *h, int nb, int minj, cudaStream_t st)
             const bool pr = (d.nSteps - 2 - it) < h->prof_steps;
             cudaError_t le = cudaSuccess;
             sr.it = it; sr.q = q; sr.pa = pa;
+            if (merged) {
+                sa.it = it; sa.q = q; sa.pa = pa;
+                const int nAdj = 1 + (sa.nWork + SW_WPB - 1) / SW_WPB, nRec = (sr.nWork + SW_WPB - 1) / SW_WPB;
+                LAUNCH(h, SEPFWI_K_STREAM_BWD, pr, st, (le = launch_pdl(k_stream_bwd, dim3(nAdj + nRec, nb), dim3(SW_NT), RC_SMEM, st, h->pdl, a, sr, sa, nAdj)));
+                CU(le);
+                q ^= 1; pa ^= 1;
+                continue;
+            }
             LAUNCH(h, SEPFWI_K_STREAM_RECON, pr, st, (le = launch_pdl(k_stream_recon, dim3((sr.nWork + SW_WPB - 1) / SW_WPB, nb), dim3(SW_NT), RC_SMEM + h->smem_pad, st, h->pdl, a, sr)));
             CU(le);
             sa.it = it; sa.q = q; sa.pa = pa;

@@ -47,7 +47,7 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
            "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots", "sepfwi_plan_resident", "sepfwi_plan_stream",
            "sepfwi_last_misfit", "sepfwi_bytes_per_slot", "sepfwi_set_data_options", "sepfwi_condition"]
-NKERNEL = 13
+NKERNEL = 14
 
 _lib = None
 

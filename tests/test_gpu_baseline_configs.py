@@ -154,7 +154,7 @@ def test_c3_single_shot_gradient_against_live_reference(tmp_path, adjacent):
         r = P.gradient(shot, [obs])
         kinds = set(P.profile())
         P.set_profile(0)
-        assert {"stream_fwd", "stream_recon", "stream_adj"} <= kinds, kinds
+        assert "stream_fwd" in kinds and ("stream_bwd" in kinds or {"stream_recon", "stream_adj"} <= kinds), kinds
     assert abs(r["misfit"] - Jr) <= 1e-4 * abs(Jr)
     tol = TOL_REF_GRAD
     if adjacent:

@@ -43,7 +43,7 @@ def run(name, batch, grad, nsteps, profile=False):
             pr = P.profile()
             print("     per-kernel us:", {k: round(1e3 * ms / n, 1) for k, (ms, n) in pr.items()})
             fk = [k for k in ("stream_fwd", "stress_fwd", "velocity_fwd") if k in pr]
-            bk = [k for k in ("stream_recon", "stream_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in pr]
+            bk = [k for k in ("stream_bwd", "stream_recon", "stream_adj", "velocity_bwd", "stress_bwd", "velocity_adj", "stress_adj") if k in pr]
             tf = sum(pr[k][0] / pr[k][1] for k in fk) * 1e-3
             if tf > 0: print("     forward step: %.1f us -> %.0f GB/s algorithmic (52 B/cell) = %.2f of 6451" % (tf * 1e6, 52 * w["live"] / tf / 1e9, 52 * w["live"] / tf / 1e9 / 6451.2))
             if bk:
