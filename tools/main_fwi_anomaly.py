@@ -24,6 +24,9 @@ ap.add_argument('--generate_data', action='store_true')
 ap.add_argument('--exp_name', type=str, default='/tmp/sepfwi-anomaly')
 ap.add_argument('--nIter', type=int, default=5)
 ap.add_argument('--ngpu', type=int, default=1)
+ap.add_argument('--model_device', default='cuda', choices=['cpu', 'cuda'],
+                help="where the model tensors of the FWI module live: 'cpu' is what the reference does (its op only takes CPU tensors); "
+                     "'cuda' keeps the parameterisation maps and the gradients on the device")
 ap.add_argument('--ref_race_compat', action='store_true', help="reproduce the reference's lost seam update in the residual injection")
 args = ap.parse_args()
 
@@ -31,6 +34,10 @@ args = ap.parse_args()
 # summed by one NCCL all-reduce, every rank then takes the identical L-BFGS step
 world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
 device = None
+if world == 1 and args.model_device == 'cuda':
+    import torch
+    if torch.cuda.is_available():
+        device = torch.device('cuda', 0)
 if world > 1:
     import torch
     import torch.distributed as td
