@@ -187,6 +187,10 @@ int sepfwi_plan_resident(const sepfwi_params *p, int nshots, int nsm, size_t sme
 /* Host-only: the work list of streaming kernel `which` (0 forward, 1 reconstruction + imaging, 2 adjoint) -- one entry per warp,
  * {first owned column, first row, end row, 1 if the warp takes the CPML path}; *n = number of entries (may exceed cap). */
 int sepfwi_plan_stream(const sepfwi_params *p, int nshots, int nsm, int which, int *items4, int cap, int *n);
+/* Host-only: the plan of the reverse-time step for `nshots` concurrent shots on `nsm` SMs.  out = {1 if the reconstruction and the
+ * adjoint sweep of a step share one launch (k_stream_bwd), jointly chosen chunk heights (adjoint interior, adjoint edge,
+ * reconstruction interior, reconstruction edge; 0 = planned separately), adjoint items per shot, reconstruction items per shot}. */
+int sepfwi_plan_backward(const sepfwi_params *p, int nshots, int nsm, int out[7]);
 int sepfwi_last_timing(sepfwi_handle *h, float *fwd_ms, float *bwd_ms);
 /* The misfit of the last sepfwi_gradient call in double precision (the float* argument mirrors the reference's float). */
 int sepfwi_last_misfit(sepfwi_handle *h, double *misfit);

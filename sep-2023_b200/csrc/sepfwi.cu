@@ -999,7 +999,8 @@ static int stream_plan(sepfwi_handle *h, int nb, int which /*0 fwd, 1 recon, 2 a
 // launch (64 shots: 1450 -> 1565 us) the adjoint CTAs only lose: the merged launch needs the reconstruction kernel's 108 KB of
 // shared memory per CTA, which leaves them a quarter of their L1.  In the latency regime the chunk heights of both sweeps are
 // chosen together: makespan of the merged grid (per shot: adjoint CTAs, then reconstruction CTAs) by list scheduling.
-static int stream_plan_pair(sepfwi_handle *h, int nb, StreamArgs &sa, StreamArgs &sr, bool &merged, cudaStream_t st)
+static int stream_plan_pair(sepfwi_handle *h, int nb, StreamArgs &sa, StreamArgs &sr, bool &merged, cudaStream_t st,
+                            std::vector<int4> *items_a = nullptr, std::vector<int4> *items_r = nullptr, int heights[4] = nullptr)
 {
     const Dims &d = h->d;
     const uint64_t want = h->staged_sig ? (h->staged_sig ^ ((uint64_t)nb << 48)) | 1ull : 0;
@@ -1030,10 +1031,12 @@ static int stream_plan_pair(sepfwi_handle *h, int nb, StreamArgs &sa, StreamArgs
             if (h->plan_debug) fprintf(stderr, "stream_plan_pair: nb %d adjoint Lz %d Le %d, reconstruction Lz %d Le %d, makespan %.1f\n", nb, h->pair_lz[2], h->pair_le[2], h->pair_lz[1], h->pair_le[1], bestc);
         }
     }
-    int rc = stream_plan(h, nb, 2, sa, st);
-    if (!rc) rc = stream_plan(h, nb, 1, sr, st);
+    if (heights) { heights[0] = h->pair_lz[2]; heights[1] = h->pair_le[2]; heights[2] = h->pair_lz[1]; heights[3] = h->pair_le[1]; }
+    int rc = stream_plan(h, nb, 2, sa, st, items_a);
+    if (!rc) rc = stream_plan(h, nb, 1, sr, st, items_r);
     h->pair_lz[1] = h->pair_lz[2] = 0;
     if (rc) return rc;
+    if (items_a) { sa.nWork = (int)items_a->size(); sr.nWork = (int)items_r->size(); }      // host-only planning: nothing was uploaded
     const double waves = (double)nb * (1 + (sa.nWork + SW_WPB - 1) / SW_WPB + (sr.nWork + SW_WPB - 1) / SW_WPB) / nslots;
     merged = h->tune_merge < 0 ? waves <= 6.5 : h->tune_merge != 0;
     return 0;
@@ -1139,6 +1142,30 @@ extern "C" int sepfwi_plan_stream(const sepfwi_params *pp, int nshots, int nsm, 
     if (rc) return rc;
     *n = (int)v.size();
     for (int i = 0; i < (int)v.size() && i < cap; i++) { items[4 * i] = v[i].x; items[4 * i + 1] = v[i].y; items[4 * i + 2] = v[i].z; items[4 * i + 3] = v[i].w; }
+    return 0;
+}
+
+// The plan of the reverse-time step `sepfwi_gradient` would use for `nshots` concurrent shots on a device with `nsm` SMs -- pure
+// host arithmetic, for tests.  out = {1 if reconstruction and adjoint sweep share one launch, jointly chosen chunk heights
+// (adjoint interior, adjoint edge, reconstruction interior, reconstruction edge; 0 = each kernel planned on its own),
+// adjoint work items per shot, reconstruction work items per shot}
+extern "C" int sepfwi_plan_backward(const sepfwi_params *pp, int nshots, int nsm, int out[7])
+{
+    if (!pp || !out || nshots < 1 || nsm < 1) return fail(SEPFWI_EINVAL, "bad argument");
+    sepfwi_handle h;
+    h.p = *pp;
+    int rc = fill_dims(*pp, h.d);
+    if (rc) return rc;
+    h.nSM = nsm;
+    StreamArgs sa, sr;
+    std::vector<int4> va, vr;
+    bool merged = false;
+    int hts[4] = {0, 0, 0, 0};
+    rc = stream_plan_pair(&h, nshots, sa, sr, merged, nullptr, &va, &vr, hts);
+    if (rc) return rc;
+    out[0] = merged ? 1 : 0;
+    for (int i = 0; i < 4; i++) out[1 + i] = hts[i];
+    out[5] = (int)va.size(); out[6] = (int)vr.size();
     return 0;
 }
 

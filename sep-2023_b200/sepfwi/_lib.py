@@ -45,7 +45,7 @@ SYMBOLS = ["sepfwi_last_error", "sepfwi_version", "sepfwi_create", "sepfwi_destr
            "sepfwi_courant", "sepfwi_forward", "sepfwi_gradient", "sepfwi_cufd", "sepfwi_cufd_clear_cache",
            "sepfwi_ring_len", "sepfwi_ring_save", "sepfwi_ring_restore", "sepfwi_get_cpml",
            "sepfwi_launch_count", "sepfwi_last_timing", "sepfwi_set_profile", "sepfwi_get_profile",
-           "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots", "sepfwi_plan_resident", "sepfwi_plan_stream",
+           "sepfwi_kernel_name", "sepfwi_resident_launches", "sepfwi_forward_snapshots", "sepfwi_plan_resident", "sepfwi_plan_stream", "sepfwi_plan_backward",
            "sepfwi_last_misfit", "sepfwi_bytes_per_slot", "sepfwi_set_data_options", "sepfwi_condition"]
 NKERNEL = 14
 
@@ -84,6 +84,7 @@ def lib():
         L.sepfwi_get_cpml.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.sepfwi_launch_count.argtypes = [C.c_void_p]
         L.sepfwi_plan_stream.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
+        L.sepfwi_plan_backward.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.sepfwi_plan_resident.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_int)]
         L.sepfwi_resident_launches.argtypes = [C.c_void_p]
         L.sepfwi_resident_launches.restype = C.c_longlong

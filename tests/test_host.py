@@ -307,3 +307,33 @@ def test_streaming_work_lists_tile_the_grid_exactly():
                 assert np.all(cover == 1), (nz, nx, nPml, nb, which)
             first_inner = np.argmax(it[:, 3] == 0) if np.any(it[:, 3] == 0) else len(it)
             assert np.all(it[first_inner:, 3] == 0)                  # edge items first
+
+
+def test_reverse_time_plan_merges_the_two_sweeps_where_the_grid_is_a_few_waves():
+    """sepfwi_plan_backward (host arithmetic only): one shot of the C3 grid and the 19-shot reference experiment are planned jointly
+    (latency regime: chunk heights of both sweeps chosen together) and run as ONE launch per reverse-time step; 8 shots of the C3
+    grid and one shot of the 8000 x 2000 grid merge without a joint plan (beyond L2); 64 shots of the C3 grid keep two launches.
+    The plan is deterministic and every work list it implies is non-empty."""
+    import ctypes as C
+    from sepfwi import _lib
+    L = _lib.lib()
+
+    def plan(nz, nx, nPml, nPad, nb):
+        p = _lib.Params(nz, nx, nPml, nPad, 100, 10.0, 10.0, 1e-3, 10.0, 0, 0, nb, 1, 1, 0, 0)
+        out = (C.c_int * 7)()
+        assert L.sepfwi_plan_backward(C.byref(p), nb, 148, out) == 0
+        return list(out)
+
+    c3 = plan(448, 1764, 32, 32, 1)      # padded C3 grid: 416 live rows + 32 alignment rows
+    assert c3[0] == 1 and all(v > 0 for v in c3[1:5]), c3
+    assert c3 == plan(448, 1764, 32, 32, 1)
+    ref = plan(224, 265, 32, 32, 19)
+    assert ref[0] == 1 and all(v > 0 for v in ref[1:5]), ref
+    c3x8 = plan(448, 1764, 32, 32, 8)
+    assert c3x8[0] == 1 and c3x8[1:5] == [0, 0, 0, 0], c3x8
+    c3x64 = plan(448, 1764, 32, 32, 64)
+    assert c3x64[0] == 0, c3x64
+    c5 = plan(2112, 8064, 32, 32, 1)
+    assert c5[0] == 1 and c5[1:5] == [0, 0, 0, 0], c5
+    for r in (c3, ref, c3x8, c3x64, c5):
+        assert r[5] > 0 and r[6] > 0
